@@ -1,0 +1,41 @@
+"""TEST INFRASTRUCTURE ONLY.  Builds oracle/_build/libnsv_oracle.so from oracle/nsv_oracle.c and,
+when /root/reference is present, oracle/_ref/libnesvor_ref_cpu.so via oracle/build_ref.sh."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "_build", "libnsv_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libnesvor_ref_cpu.so")
+# not $CC: this image presets it to a wrapper that cannot find libgomp.spec
+GCC = os.environ.get("NSV_CC", "/usr/bin/gcc")
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build_oracle(force=False):
+    srcs = [os.path.join(HERE, f) for f in ("nsv_oracle.c", "slice_acq_oracle_impl.h", "transform_oracle_impl.h")]
+    if force or _stale(ORACLE_SO, srcs):
+        os.makedirs(os.path.dirname(ORACLE_SO), exist_ok=True)
+        cmd = [GCC, "-O2", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-std=gnu11",
+               "-o", ORACLE_SO, srcs[0], "-lm"]
+        subprocess.check_call(cmd)
+    return ORACLE_SO
+
+
+def build_ref(force=False):
+    """Returns the path of the CPU build of the reference kernels, or None if it cannot exist."""
+    ref_root = os.environ.get("NSV_REFERENCE_ROOT", "/root/reference")
+    srcs = [os.path.join(HERE, f) for f in ("build_ref.sh", "ref_cpu_shim.h", "ref_driver_slice_acq.inc", "ref_driver_transform.inc")]
+    if os.path.isdir(ref_root) and (force or _stale(REF_SO, srcs)):
+        subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")])
+    return REF_SO if os.path.exists(REF_SO) else None
+
+
+if __name__ == "__main__":
+    print(build_oracle(force=True))
+    print(build_ref(force=True))
