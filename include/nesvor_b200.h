@@ -1,0 +1,221 @@
+/*
+ * nesvor_b200.h -- C ABI of libnesvor_b200.so (sm_100a), the drop-in boundary for NeSVoR's
+ * reconstruction hot path.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is DEVICE memory unless the parameter name starts with "h_";
+ *   - inputs are borrowed, outputs are caller-allocated; entry points never allocate and never
+ *     synchronise; work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream, which is what the reference's extensions always use);
+ *   - optional pointers may be NULL (the reference passes empty tensors for absent masks,
+ *     nesvor/slice_acquisition/slice_acq.py:36-39);
+ *   - return value: 0 on success, otherwise a cudaError_t (launch/config error) or a negative
+ *     NSV_E* code for invalid arguments.  nsv_last_error_string() describes the last failure on
+ *     the calling thread.
+ *   - bool masks are 1 byte per element (torch.bool).
+ *
+ * Each block cites the reference interface it replaces (paths relative to /root/reference).
+ */
+#ifndef NESVOR_B200_H_
+#define NESVOR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSV_OK 0
+#define NSV_EINVAL (-1)      /* bad argument (NULL where required, non-positive size, ...) */
+#define NSV_EUNSUPPORTED (-2) /* configuration outside what the kernels are instantiated for */
+
+#define NSV_MAX_LEVELS 32
+
+int nsv_version(void);                     /* ABI version, currently 1 */
+const char* nsv_last_error_string(void);   /* thread-local, never NULL */
+const char* nsv_build_arch(void);          /* "sm_100a" */
+
+/* ------------------------------------------------------------------------------------------
+ * Rigid-pose converters.  Replaces nesvor.transform_convert_cuda.{axisangle2mat_forward,
+ * axisangle2mat_backward, mat2axisangle_forward, mat2axisangle_backward}
+ * (nesvor/transform/transform_convert_cuda.cpp:27-69; kernels transform_convert_cuda_kernel.cu:15-440).
+ * axisangle: [n,6] = (rx,ry,rz,tx,ty,tz); mat: [n,3,4] row-major [R|t].  Outputs fully written.
+ * ------------------------------------------------------------------------------------------ */
+int nsv_axisangle2mat_fwd_f32(const float* axisangle, float* mat, int n, void* stream);
+int nsv_axisangle2mat_bwd_f32(const float* grad_mat, const float* axisangle, float* grad_axisangle, int n, void* stream);
+int nsv_mat2axisangle_fwd_f32(const float* mat, float* axisangle, int n, void* stream);
+int nsv_mat2axisangle_bwd_f32(const float* mat, const float* grad_axisangle, float* grad_mat, int n, void* stream);
+int nsv_axisangle2mat_fwd_f64(const double* axisangle, double* mat, int n, void* stream);
+int nsv_axisangle2mat_bwd_f64(const double* grad_mat, const double* axisangle, double* grad_axisangle, int n, void* stream);
+int nsv_mat2axisangle_fwd_f64(const double* mat, double* axisangle, int n, void* stream);
+int nsv_mat2axisangle_bwd_f64(const double* mat, const double* grad_axisangle, double* grad_mat, int n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Slice acquisition (PSF-weighted gather A, scatter A^T and their backward passes).  Replaces
+ * nesvor.slice_acq_cuda.{forward, backward, adjoint_forward, adjoint_backward}
+ * (nesvor/slice_acquisition/slice_acq_cuda.cpp:61-160; kernels slice_acq_cuda_kernel.cu:18-950).
+ *   transforms [n,3,4] (voxel units), vol [D,H,W], psf [d_p,h_p,w_p], slices [n,h,w].
+ * Unlike the reference's host wrappers, outputs are NOT zero-filled here when the op only writes
+ * part of them: the caller passes zero-initialised `slices`, `slices_weight`, `grad_vol`,
+ * `grad_transforms`, `vol`, `vol_weight`, `grad_slices` (torch.zeros), exactly as
+ * slice_acq_cuda_kernel.cu:965-966,1005-1006,1040-1041,1109-1110 allocate them.
+ * nsv_slice_acq_adjoint_forward runs the equalize pass itself when `equalize` != 0;
+ * nsv_slice_acq_adjoint_backward first equalizes `grad_vol` IN PLACE when `equalize` != 0
+ * (slice_acq_cuda_kernel.cu:1095-1107), as the reference does.
+ * ------------------------------------------------------------------------------------------ */
+int nsv_slice_acq_forward_f32(const float* transforms, const float* vol, const uint8_t* vol_mask,
+                              const uint8_t* slices_mask, const float* psf, float* slices, float* slices_weight,
+                              int D, int H, int W, int d_p, int h_p, int w_p, int n, int h, int w,
+                              float res_slice, int interp_psf, void* stream);
+int nsv_slice_acq_backward_f32(const float* transforms, const float* vol, const uint8_t* vol_mask, const float* psf,
+                               const float* grad_slices, const uint8_t* slices_mask, float* grad_vol,
+                               float* grad_transforms, int D, int H, int W, int d_p, int h_p, int w_p, int n, int h,
+                               int w, float res_slice, int interp_psf, void* stream);
+int nsv_slice_acq_adjoint_forward_f32(const float* transforms, const float* psf, const float* slices,
+                                      const uint8_t* slices_mask, const uint8_t* vol_mask, float* vol,
+                                      float* vol_weight, int D, int H, int W, int d_p, int h_p, int w_p, int n, int h,
+                                      int w, float res_slice, int interp_psf, int equalize, void* stream);
+int nsv_slice_acq_adjoint_backward_f32(const float* transforms, float* grad_vol, const float* vol_weight,
+                                       const uint8_t* vol_mask, const float* psf, const float* slices,
+                                       const uint8_t* slices_mask, const float* vol, float* grad_slices,
+                                       float* grad_transforms, int D, int H, int W, int d_p, int h_p, int w_p, int n,
+                                       int h, int w, float res_slice, int interp_psf, int equalize, void* stream);
+int nsv_equalize_f32(float* vol, const float* vol_weight, int is_grad, int64_t DHW, void* stream);
+
+int nsv_slice_acq_forward_f64(const double* transforms, const double* vol, const uint8_t* vol_mask,
+                              const uint8_t* slices_mask, const double* psf, double* slices, double* slices_weight,
+                              int D, int H, int W, int d_p, int h_p, int w_p, int n, int h, int w,
+                              double res_slice, int interp_psf, void* stream);
+int nsv_slice_acq_backward_f64(const double* transforms, const double* vol, const uint8_t* vol_mask, const double* psf,
+                               const double* grad_slices, const uint8_t* slices_mask, double* grad_vol,
+                               double* grad_transforms, int D, int H, int W, int d_p, int h_p, int w_p, int n, int h,
+                               int w, double res_slice, int interp_psf, void* stream);
+int nsv_slice_acq_adjoint_forward_f64(const double* transforms, const double* psf, const double* slices,
+                                      const uint8_t* slices_mask, const uint8_t* vol_mask, double* vol,
+                                      double* vol_weight, int D, int H, int W, int d_p, int h_p, int w_p, int n, int h,
+                                      int w, double res_slice, int interp_psf, int equalize, void* stream);
+int nsv_slice_acq_adjoint_backward_f64(const double* transforms, double* grad_vol, const double* vol_weight,
+                                       const uint8_t* vol_mask, const double* psf, const double* slices,
+                                       const uint8_t* slices_mask, const double* vol, double* grad_slices,
+                                       double* grad_transforms, int D, int H, int W, int d_p, int h_p, int w_p, int n,
+                                       int h, int w, double res_slice, int interp_psf, int equalize, void* stream);
+int nsv_equalize_f64(double* vol, const double* vol_weight, int is_grad, int64_t DHW, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Multiresolution hash-grid encoding.  Replaces tcnn.Encoding(HashGrid) as used through
+ * build_encoding (nesvor/nesvor/models.py:22-25, built :102-111, called :146); tiny-cuda-nn is an
+ * external dependency of the reference (README.md:88), semantics per SURVEY.md App. A.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct nsv_grid_meta {
+  int32_t n_levels;
+  int32_t n_features;                  /* F: 1, 2, 4 or 8 */
+  float scale[NSV_MAX_LEVELS];         /* base * s^l - 1 (fp32) */
+  uint32_t res[NSV_MAX_LEVELS];        /* ceil(scale)+1 */
+  uint32_t size[NSV_MAX_LEVELS];       /* entries in the level, T_l */
+  uint32_t offset[NSV_MAX_LEVELS + 1]; /* first entry of the level in the flat table */
+  uint32_t hashed[NSV_MAX_LEVELS];     /* 1: XOR-prime hash, 0: dense */
+} nsv_grid_meta;
+
+/* host helper: fills `meta` from the tcnn-style hyper-parameters; returns total entry count */
+int64_t nsv_grid_meta_init(nsv_grid_meta* h_meta, int n_levels, int n_features, int log2_hashmap_size,
+                           int base_resolution, float per_level_scale);
+
+/* x [N,3] fp32 in [0,1] (unclamped); table: flat [sum T_l, F] (fp32 or fp16 copy);
+ * out [N, L*F] level-major (fp32 or fp16).  `dy_dx` (optional, [N, L*F, 3] fp32) receives
+ * d out / d x for nsv_hashgrid_bwd_input. */
+int nsv_hashgrid_fwd_f32(const float* x, const float* table, const nsv_grid_meta* h_meta, float* out, int64_t N, void* stream);
+int nsv_hashgrid_fwd_f16(const float* x, const void* table_f16, const nsv_grid_meta* h_meta, void* out_f16, int64_t N, void* stream);
+/* grad_table (fp32, flat, same layout as table) += scatter of grad_out; caller zero-fills */
+int nsv_hashgrid_bwd_params_f32(const float* x, const float* grad_out, const nsv_grid_meta* h_meta, float* grad_table, int64_t N, void* stream);
+int nsv_hashgrid_bwd_params_f16(const float* x, const void* grad_out_f16, const nsv_grid_meta* h_meta, float* grad_table, float grad_scale, int64_t N, void* stream);
+/* grad_x [N,3] = sum_l d out_l / d x * grad_out_l (recomputed from the table, nothing stored) */
+int nsv_hashgrid_bwd_input_f32(const float* x, const float* table, const float* grad_out, const nsv_grid_meta* h_meta, float* grad_x, int64_t N, void* stream);
+int nsv_hashgrid_bwd_input_f16(const float* x, const void* table_f16, const void* grad_out_f16, const nsv_grid_meta* h_meta, float grad_scale, float* grad_x, int64_t N, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fully fused small MLP (fp16 operands, fp32 accumulate, ReLU hidden, linear output, no biases).
+ * Replaces tcnn.Network(CutlassMLP) as used through build_network's fp16 branch
+ * (nesvor/nesvor/models.py:28-41; instances :113-121, :238-258).
+ * weights: fp16, layers concatenated, layer i row-major [out_i, in_i]; n_in / n_out padded to 16,
+ * width in {16, 32, 64, 128}; n_hidden >= 1.
+ * ------------------------------------------------------------------------------------------ */
+int nsv_mlp_fwd_f16(const void* x_f16, const void* weights_f16, void* out_f16, void* hidden_f16 /* [n_hidden, N, width] or NULL */,
+                    int64_t N, int n_in, int n_out, int width, int n_hidden, void* stream);
+int nsv_mlp_bwd_f16(const void* x_f16, const void* weights_f16, const void* hidden_f16, const void* grad_out_f16,
+                    void* grad_x_f16 /* or NULL */, float* grad_weights /* fp32, same layout, caller zero-fills */,
+                    int64_t N, int n_in, int n_out, int width, int n_hidden, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Kernel A: one fused NeSVoR training iteration (forward + loss + backward) over a batch of B
+ * slice pixels x S PSF samples, and the forward-only renderer.
+ * Replaces the op sequence NeSVoR.forward -> net_forward -> INR.forward -> losses -> autograd
+ * backward (nesvor/nesvor/models.py:260-384, called from train.py:183-190) and
+ * INR.sample_batch + INR.forward(...).mean(-1) (models.py:142-174, sample.py:17-53).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct nsv_inr_config {
+  nsv_grid_meta grid;
+  int32_t width;            /* hidden width W: 32 or 64 */
+  int32_t depth;            /* hidden layers per MLP (args.depth), 1..4 */
+  int32_t n_features_z;     /* 15 */
+  int32_t n_features_slice; /* 16 (0 disables the embedding) */
+  int32_t n_levels_bias;    /* 0 disables b_net */
+  int32_t pixel_variance;   /* sigma_net on */
+  int32_t slice_variance;
+  int32_t slice_scale;
+  int32_t pose_grad;        /* back-propagate into axisangle */
+  int32_t image_reg;        /* 0 none, 1 TV, 2 edge, 3 L2 */
+  float delta;              /* args.delta * v_mean */
+  float w_image;            /* loss weights (train.py:167-173); MSE and logVar have weight 1 */
+  float w_bias;
+  float bbox_lo[3], bbox_hi[3];
+  float grad_scale;         /* power of two applied to fp16 backward operands (loss scale) */
+} nsv_inr_config;
+
+typedef struct nsv_inr_params {   /* device pointers */
+  const void* table_f16;          /* [sum T_l, F] fp16 copy of the master table */
+  const void* mlp_f16;            /* packed fp16 weights, see nsv_inr_mlp_layout() */
+  const float* axisangle;         /* [n_slices, 6] */
+  const float* psf_sigma;         /* [n_slices, 3] */
+  const float* slice_embedding;   /* [n_slices, n_features_slice] or NULL */
+  const float* logit_coef;        /* [n_slices] or NULL */
+  const float* log_var_slice;     /* [n_slices] or NULL */
+  int32_t n_slices;
+} nsv_inr_params;
+
+typedef struct nsv_inr_grads {    /* device pointers, all fp32, caller zero-fills before the call */
+  float* table;                   /* same layout as the table */
+  float* mlp;                     /* same layout as mlp_f16 (element for element) */
+  float* axisangle;               /* [n_slices, 6] or NULL */
+  float* slice_embedding;
+  float* slice_scale_c;           /* [n_slices]: dL/dc_k (softmax chain rule left to the caller) */
+  float* log_var_slice;
+  float* losses;                  /* [8]: MSE, logVar, biasReg(sum log_bias), imageReg, ... as partial sums */
+} nsv_inr_grads;
+
+/* number of fp16 elements of the packed MLP buffer and per-net offsets (host helper) */
+int64_t nsv_inr_mlp_layout(const nsv_inr_config* h_cfg, int64_t* h_offsets /* [3]: density, sigma, bias */);
+
+int nsv_inr_train_step(const nsv_inr_config* h_cfg, const nsv_inr_params* h_params, const nsv_inr_grads* h_grads,
+                       const float* xyz /* [B,3] */, const float* v /* [B] */, const int64_t* slice_idx /* [B] */,
+                       const float* noise /* [B,S,3] or NULL -> in-kernel Philox(seed, offset) */,
+                       uint64_t seed, uint64_t offset, float* v_out /* [B] or NULL */, int64_t B, int S, void* stream);
+
+int nsv_inr_render(const nsv_inr_config* h_cfg, const nsv_inr_params* h_params,
+                   const float* xyz /* [M,3] */, const float* mat /* [M,3,4] per-point or [1,3,4] or NULL */, int mat_per_point,
+                   const float* psf_sigma /* [M,3] per-point or [3] */, int sigma_per_point,
+                   const float* noise /* [M,S,3] or NULL */, uint64_t seed, uint64_t offset,
+                   float* out /* [M] mean density */, int64_t M, int S, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser: fused AdamW over a flat fp32 segment, optionally refreshing an fp16 copy.
+ * Replaces torch.optim.AdamW as configured in nesvor/nesvor/train.py:134-152 (+ GradScaler
+ * unscale, train.py:162-164,195).
+ * ------------------------------------------------------------------------------------------ */
+int nsv_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_f16 /* or NULL */,
+                   int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                   float grad_unscale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NESVOR_B200_H_ */

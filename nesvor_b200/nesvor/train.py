@@ -1,0 +1,167 @@
+"""Training driver of the INR path: pixel table, optimiser, hot loop.
+
+Host-side mirror of nesvor/nesvor/train.py: `Dataset` (:14-120: pixel table, `bounding_box`, `mean`,
+`get_batch` with full-table reshuffle at epoch end, `mask`) and `train(slices, args)` (:123-232:
+AdamW with two groups, MultiStepLR on milestones, GradScaler(init_scale=1), loss weights, logging
+of moving averages, outputs).  The per-iteration compute is delegated to `NeSVoR.forward`
+(autograd-composed native ops) or, when `args.fused` is set and the configuration is supported,
+to the fused kernel + fused AdamW (`fused.FusedTrainer`).
+"""
+from argparse import Namespace
+from typing import Dict, List, Tuple
+import datetime
+import logging
+import time
+
+import torch
+import torch.optim as optim
+
+from ..image import Slice, Volume
+from ..transform import RigidTransform, transform_points
+from ..utils import MovingAverage, gaussian_blur
+from .models import B_REG, D_LOSS, DS_LOSS, I_REG, INR, S_LOSS, T_REG, NeSVoR
+
+
+class Dataset(object):
+    def __init__(self, slices: List[Slice], args: Namespace) -> None:
+        self.mask_threshold = getattr(args, "mask_threshold", 1.0)
+        xyz_all, v_all, slice_idx_all, transformation_all, resolution_all = [], [], [], [], []
+        for i, s in enumerate(slices):
+            v = s.v_masked
+            xyz_all.append(s.xyz_masked_untransformed)
+            v_all.append(v)
+            slice_idx_all.append(torch.full(v.shape, i, device=v.device))
+            transformation_all.append(s.transformation)
+            resolution_all.append(s.resolution_xyz)
+        self.xyz = torch.cat(xyz_all)
+        self.v = torch.cat(v_all)
+        self.slice_idx = torch.cat(slice_idx_all)
+        self.transformation = RigidTransform.cat(transformation_all)
+        self.resolution = torch.stack(resolution_all, 0)
+        self.count = self.v.shape[0]
+        self.epoch = 0
+
+    @property
+    def xyz_transformed(self) -> torch.Tensor:
+        return transform_points(self.transformation[self.slice_idx], self.xyz)
+
+    @property
+    def bounding_box(self) -> torch.Tensor:
+        max_r = self.resolution.max()
+        xyz = self.xyz_transformed
+        return torch.stack([xyz.amin(0) - 2 * max_r, xyz.amax(0) + 2 * max_r], 0)
+
+    @property
+    def mean(self) -> float:
+        v = self.v if self.v.numel() < 256**3 else self.v[: 256**3]
+        q1, q2 = torch.quantile(v, torch.tensor([0.1, 0.9], dtype=v.dtype, device=v.device))
+        return self.v[torch.logical_and(self.v > q1, self.v < q2)].mean().item()
+
+    def get_batch(self, batch_size: int, device) -> Dict[str, torch.Tensor]:
+        if self.count + batch_size > self.xyz.shape[0]:  # new epoch: shuffle the whole table
+            self.count = 0
+            self.epoch += 1
+            idx = torch.randperm(self.xyz.shape[0], device=device)
+            self.xyz, self.v, self.slice_idx = self.xyz[idx], self.v[idx], self.slice_idx[idx]
+        sl = slice(self.count, self.count + batch_size)
+        self.count += batch_size
+        return {"xyz": self.xyz[sl], "v": self.v[sl], "slice_idx": self.slice_idx[sl]}
+
+    @property
+    def mask(self) -> Volume:
+        """Occupancy mask of the transformed pixel cloud: bincount + separable blur (train.py:82-120)."""
+        with torch.no_grad():
+            r_min, r_max = self.resolution.min(), self.resolution.max()
+            xyz = self.xyz_transformed
+            xyz_min = xyz.amin(0) - r_max * 10
+            xyz_max = xyz.amax(0) + r_max * 10
+            shape_xyz = ((xyz_max - xyz_min) / r_min).ceil().long()
+            shape = (int(shape_xyz[2]), int(shape_xyz[1]), int(shape_xyz[0]))
+            kji = ((xyz - xyz_min) / r_min).round().long()
+            flat = kji[..., 0] + shape[2] * kji[..., 1] + shape[2] * shape[1] * kji[..., 2]
+            mask = torch.bincount(flat, minlength=shape[0] * shape[1] * shape[2]).view((1, 1) + shape).float()
+            thr = self.mask_threshold * r_min**3 / self.resolution.log().mean().exp() ** 3
+            thr = thr * (mask.sum() / (mask > 0).sum())
+            mask = (gaussian_blur(mask, (r_max / r_min).item(), 3) > thr)[0, 0]
+            xyz_c = xyz_min + (shape_xyz - 1) / 2 * r_min
+            return Volume(mask.float(), mask, RigidTransform(torch.cat([0 * xyz_c, xyz_c])[None], True), r_min, r_min, r_min)
+
+
+def build_optimizer(model: torch.nn.Module, args: Namespace):
+    """AdamW with the reference's two parameter groups (train.py:134-152)."""
+    params_net, params_encoding = [], []
+    for name, param in model.named_parameters():
+        if param.numel() > 0:
+            (params_net if "_net" in name else params_encoding).append(param)
+    return torch.optim.AdamW(
+        params=[{"name": "encoding", "params": params_encoding}, {"name": "net", "params": params_net, "weight_decay": 1e-2}],
+        lr=args.learning_rate, betas=(0.9, 0.99), eps=1e-15)
+
+
+def loss_weights(args: Namespace) -> Dict[str, float]:
+    return {D_LOSS: 1, S_LOSS: 1, T_REG: args.weight_transformation, B_REG: args.weight_bias, I_REG: args.weight_image}
+
+
+def train(slices: List[Slice], args: Namespace) -> Tuple[INR, List[Slice], Volume]:
+    dataset = Dataset(slices, args)
+    model = NeSVoR(dataset.transformation, dataset.resolution, dataset.mean, dataset.bounding_box, args)
+    use_fused = bool(getattr(args, "fused", False))
+    if use_fused:
+        from .fused import FusedTrainer
+
+        trainer = FusedTrainer(model, args)
+    else:
+        optimizer = build_optimizer(model, args)
+        scheduler = optim.lr_scheduler.MultiStepLR(optimizer=optimizer, milestones=list(range(1, len(args.milestones) + 1)), gamma=args.gamma)
+        fp16 = not args.single_precision
+        scaler = torch.amp.GradScaler("cuda", init_scale=1.0, enabled=fp16, growth_factor=2.0, backoff_factor=0.5)
+    decay_milestones = [int(m * args.n_iter) for m in args.milestones]
+    model.train()
+    weights = loss_weights(args)
+    average = MovingAverage(1 - 0.001)
+    logging.info("NeSVoR training starts.")
+    train_time = 0.0
+    for i in range(1, args.n_iter + 1):
+        t0 = time.time()
+        batch = dataset.get_batch(args.batch_size, args.device)
+        if use_fused:
+            losses = trainer.step(**batch)
+        else:
+            losses = model(**batch)
+            loss = 0
+            for k in losses:
+                if k in weights and weights[k]:
+                    loss = loss + weights[k] * losses[k]
+            scaler.scale(loss).backward()
+            if getattr(args, "debug", False):
+                for _name, _p in model.named_parameters():
+                    if _p.grad is not None and not _p.grad.isfinite().all():
+                        logging.debug("iter %d: Found NaNs in the grad of %s", i, _name)
+            scaler.step(optimizer)
+            scaler.update()
+            optimizer.zero_grad()
+        train_time += time.time() - t0
+        if not getattr(args, "no_loss_sync", False):
+            for k in losses:
+                average(k, losses[k].item())
+        if (decay_milestones and i >= decay_milestones[0]) or i == args.n_iter:
+            lr = trainer.lr if use_fused else optimizer.param_groups[0]["lr"]
+            logging.info("time %s epoch %d iter %d %s lr %.3e", datetime.timedelta(seconds=int(train_time)), dataset.epoch, i,
+                         " ".join("%s=%.4e" % (k, average[k]) for k in losses), lr)
+            if i < args.n_iter:
+                decay_milestones.pop(0)
+                if use_fused:
+                    trainer.decay_lr(args.gamma)
+                else:
+                    scheduler.step()
+    if use_fused:
+        trainer.sync_to_model()
+    transformation = model.transformation
+    dataset.transformation = transformation
+    mask = dataset.mask
+    output_slices = []
+    for i in range(len(slices)):
+        output_slice = slices[i].clone()
+        output_slice.transformation = transformation[i]
+        output_slices.append(output_slice)
+    return model.inr, output_slices, mask

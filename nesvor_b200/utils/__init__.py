@@ -1,0 +1,2 @@
+from .psf import GAUSSIAN_FWHM, SINC_FWHM, resolution2sigma, get_PSF
+from .misc import meshgrid, gaussian_blur, MovingAverage

@@ -227,7 +227,8 @@ void FN(nsv_oracle_slice_acq_backward_)(const REAL* transforms, const REAL* vol,
   const long npx = (long)n * h * w;
   if (grad_vol) memset(grad_vol, 0, (size_t)D * H * W * sizeof(REAL));
   if (grad_transforms) memset(grad_transforms, 0, (size_t)n * 12 * sizeof(REAL));
-  for (long idx = 0; idx < npx; ++idx) { /* serial: scatter target is shared */
+#pragma omp parallel for schedule(static)
+  for (long idx = 0; idx < npx; ++idx) { /* scatter: atomics; 1 thread == serial order */
     if (slices_mask && !slices_mask[idx]) continue;
     REAL gs = grad_slices[idx];
     if (gs == 0) continue; /* Q2 */
@@ -244,7 +245,11 @@ void FN(nsv_oracle_slice_acq_backward_)(const REAL* transforms, const REAL* vol,
       FN(NearestTap) t;
       if (!FN(nearest_tap)(&f, p, sy, sz, d_p, h_p, w_p, &t)) continue;
       if (vol_mask && !vol_mask[t.vox]) continue;
-      if (grad_vol) grad_vol[t.vox] += FN(psf_resampled)(psf, &t.pc) * gs;
+      if (grad_vol) {
+        const REAL add = FN(psf_resampled)(psf, &t.pc) * gs;
+#pragma omp atomic
+        grad_vol[t.vox] += add;
+      }
       if (grad_transforms) {
         REAL d[3] = {0, 0, 0};
         for (int k = 0; k < 8; ++k) {
@@ -264,7 +269,9 @@ void FN(nsv_oracle_slice_acq_backward_)(const REAL* transforms, const REAL* vol,
           const int c = FN(kCornerOrder)[k];
           const int iv = cell.base + cell.off[c];
           if (vol_mask && !vol_mask[iv]) continue;
-          grad_vol[iv] += cell.wt[c] * tap;
+          const REAL add = cell.wt[c] * tap;
+#pragma omp atomic
+          grad_vol[iv] += add;
         }
       if (grad_transforms) {
         REAL d[3] = {0, 0, 0};
@@ -279,7 +286,10 @@ void FN(nsv_oracle_slice_acq_backward_)(const REAL* transforms, const REAL* vol,
     }
     NSV_TAP_LOOP_END
     if (grad_transforms)
-      for (int k = 0; k < 12; ++k) grad_transforms[is * 12 + k] += acc.g[k];
+      for (int k = 0; k < 12; ++k) {
+#pragma omp atomic
+        grad_transforms[is * 12 + k] += acc.g[k];
+      }
   }
 }
 
@@ -308,6 +318,7 @@ void FN(nsv_oracle_slice_acq_adjoint_forward_)(const REAL* transforms, const REA
   memset(vol, 0, (size_t)nvx * sizeof(REAL));
   REAL* vw = equalize ? vol_weight : NULL;
   if (vw) memset(vw, 0, (size_t)nvx * sizeof(REAL));
+#pragma omp parallel for schedule(static)
   for (long idx = 0; idx < npx; ++idx) {
     if (slices_mask && !slices_mask[idx]) continue;
     const REAL s = slices[idx];
@@ -323,8 +334,15 @@ void FN(nsv_oracle_slice_acq_adjoint_forward_)(const REAL* transforms, const REA
       tap = FN(psf_resampled)(psf, &t.pc);
       tap /= weight;
       if (vol_mask && !vol_mask[t.vox]) continue;
-      vol[t.vox] += tap * s;
-      if (vw) vw[t.vox] += tap;
+      {
+        const REAL add = tap * s;
+#pragma omp atomic
+        vol[t.vox] += add;
+      }
+      if (vw) {
+#pragma omp atomic
+        vw[t.vox] += tap;
+      }
     } else {
       FN(Cell) cell;
       FN(cell_at)(p, sy, sz, &cell);
@@ -334,8 +352,13 @@ void FN(nsv_oracle_slice_acq_adjoint_forward_)(const REAL* transforms, const REA
         const int iv = cell.base + cell.off[c];
         if (vol_mask && !vol_mask[iv]) continue;
         const REAL pw = cell.wt[c] * tap;
-        vol[iv] += pw * s;
-        if (vw) vw[iv] += pw;
+        const REAL add = pw * s;
+#pragma omp atomic
+        vol[iv] += add;
+        if (vw) {
+#pragma omp atomic
+          vw[iv] += pw;
+        }
       }
     }
     NSV_TAP_LOOP_END
@@ -355,6 +378,7 @@ void FN(nsv_oracle_slice_acq_adjoint_backward_)(
   const REAL* resid = equalize ? vol : NULL;
   if (grad_slices) memset(grad_slices, 0, (size_t)npx * sizeof(REAL));
   if (grad_transforms) memset(grad_transforms, 0, (size_t)n * 12 * sizeof(REAL));
+#pragma omp parallel for schedule(static)
   for (long idx = 0; idx < npx; ++idx) {
     if (slices_mask && !slices_mask[idx]) continue;
     const int ix = (int)(idx % w), iy = (int)((idx / w) % h), is = (int)(idx / ((long)h * w));
@@ -413,7 +437,11 @@ void FN(nsv_oracle_slice_acq_adjoint_backward_)(
     if (weight > 0) {
       if (grad_slices) grad_slices[idx] = val / weight;
       if (grad_transforms)
-        for (int k = 0; k < 12; ++k) grad_transforms[is * 12 + k] += acc.g[k] / weight;
+        for (int k = 0; k < 12; ++k) {
+          const REAL add = acc.g[k] / weight;
+#pragma omp atomic
+          grad_transforms[is * 12 + k] += add;
+        }
     }
   }
 }

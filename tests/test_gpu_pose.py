@@ -1,0 +1,74 @@
+"""GPU parity: native pose converters (through the C ABI) vs the reference goldens and the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import REF_AXISANGLES, scipy_axisangle2mat
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_reference_golden_vectors(native_lib):
+    import nesvor_b200 as nb
+
+    for row in REF_AXISANGLES:  # one row at a time, like tests/transform/test_transform_convert.py:13-21
+        ax = torch.tensor([row], dtype=torch.float32).cuda()
+        mat = torch.from_numpy(scipy_axisangle2mat(ax.cpu().numpy())).cuda()
+        torch.testing.assert_close(nb.axisangle2mat(ax), mat)
+        torch.testing.assert_close(nb.mat2axisangle(mat), ax)
+
+
+def test_against_reference_kernel_outputs(native_lib):
+    """tests/golden/pose_ref.npz = the reference's own kernels run on CPU; tolerance = fp32 libm
+    differences between glibc and CUDA (sinf/cosf/atan2f <= 2 ulp) amplified by |t| ~ 1."""
+    import nesvor_b200.transform.transform_convert as tc
+
+    g = {k: torch.from_numpy(v).cuda() for k, v in np.load(os.path.join(GOLD, "pose_ref.npz")).items()}
+    torch.testing.assert_close(tc.axisangle2mat_forward(g["axisangle"])[0], g["mat"], atol=2e-6, rtol=1e-5)
+    torch.testing.assert_close(tc.axisangle2mat_backward(g["grad_mat"], g["axisangle"])[0], g["a2m_bwd"], atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(tc.mat2axisangle_forward(g["mat"])[0], g["m2a_fwd"], atol=2e-5, rtol=1e-4)
+    # near-pi rows amplify 1-ulp input differences; compare the bulk tightly and everything loosely
+    torch.testing.assert_close(tc.mat2axisangle_backward(g["mat"], g["grad_axisangle"])[0], g["m2a_bwd"], atol=5e-2, rtol=1e-2)
+    bulk = slice(11, None)
+    torch.testing.assert_close(tc.mat2axisangle_backward(g["mat"][bulk].contiguous(), g["grad_axisangle"][bulk].contiguous())[0],
+                               g["m2a_bwd"][bulk], atol=2e-4, rtol=1e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_against_oracle_random(native_lib, oracle, dtype):
+    import nesvor_b200.transform.transform_convert as tc
+
+    rng = np.random.default_rng(0)
+    npdt = np.float32 if dtype == torch.float32 else np.float64
+    ax = rng.normal(size=(4096, 6)).astype(npdt)
+    ax[:64, :3] *= 1e-4
+    axc = torch.from_numpy(ax).cuda()
+    mat = tc.axisangle2mat_forward(axc)[0]
+    torch.testing.assert_close(mat.cpu(), torch.from_numpy(oracle.axisangle2mat_forward(ax)[0]), atol=2e-6, rtol=1e-5)
+    gm = rng.normal(size=(4096, 3, 4)).astype(npdt)
+    torch.testing.assert_close(tc.axisangle2mat_backward(torch.from_numpy(gm).cuda(), axc)[0].cpu(),
+                               torch.from_numpy(oracle.axisangle2mat_backward(gm, ax)[0]), atol=5e-5, rtol=1e-4)
+    m_np = mat.cpu().numpy()
+    torch.testing.assert_close(tc.mat2axisangle_forward(mat)[0].cpu(), torch.from_numpy(oracle.mat2axisangle_forward(m_np)[0]), atol=5e-5, rtol=1e-4)
+
+
+def test_autograd_and_rigid_transform(native_lib):
+    import nesvor_b200 as nb
+
+    ax = torch.tensor(REF_AXISANGLES, dtype=torch.float32).cuda()
+    zeros = torch.zeros(1, 6, device="cuda")
+    for i in range(len(ax)):  # compose / inv identity, tests/transform/test_transform.py:7-23
+        a, b = ax[i : i + 1].contiguous(), ax[len(ax) - 1 - i : len(ax) - i].contiguous()
+        ma, mb = nb.axisangle2mat(a), nb.axisangle2mat(b)
+        ab = nb.RigidTransform(a, trans_first=i % 2 == 0).compose(nb.RigidTransform(mb, trans_first=i % 2 == 1))
+        binv_ainv = nb.RigidTransform(b, trans_first=i % 2 == 1).inv().compose(nb.RigidTransform(ma, trans_first=i % 2 == 0).inv())
+        torch.testing.assert_close(ab.compose(binv_ainv).axisangle(), zeros, atol=2e-5, rtol=1e-3)
+    x = torch.randn(16, 6, device="cuda", dtype=torch.float64, requires_grad=True)
+    # analytic backward kernels vs numerical differentiation (trig is single precision inside)
+    assert torch.autograd.gradcheck(nb.axisangle2mat, (x,), eps=1e-3, atol=1e-3, rtol=1e-3, nondet_tol=0)
+    assert nb.axisangle2mat(torch.zeros(0, 6, device="cuda")).shape == (0, 3, 4)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        nb.axisangle2mat(torch.zeros(6, 4, device="cuda").t())

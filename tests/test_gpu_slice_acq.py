@@ -1,0 +1,158 @@
+"""GPU parity for kernel B through the C ABI: native slice acquisition family vs the reference's
+golden outputs, vs the C oracle on seeded inputs, the reference's CG known-answer test, and the
+adjointness property at BASELINE sizes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import cuda, gaussian_psf, rel_l2, slice_acq_case
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+# forward / adjoint-backward are gathers computed with the reference's exact fp32 expression order
+# (-fmad=false): expected bit-exact; scatter passes (float atomics, non-deterministic order) and the
+# CTA-reduced pose gradients are compared at fp32 round-off.
+GATHER_TOL = dict(atol=0, rtol=0)
+SCATTER_TOL = dict(atol=2e-5, rtol=2e-4)
+
+
+def _native_all(c, interp):
+    import nesvor_b200.slice_acquisition.slice_acq as sa
+
+    tf, vol, psf = cuda(c["transforms"]), cuda(c["vol"]), cuda(c["psf"])
+    vm, sm = cuda(c["vol_mask"]), cuda(c["slices_mask"])
+    out = {}
+    out["slices"], out["weight"] = sa.forward(tf, vol, vm, sm, psf, c["slice_shape"], c["res_slice"], True, interp)
+    out["bwd_grad_vol"], out["bwd_grad_tf"] = sa.backward(tf, vol, vm, psf, cuda(c["grad_slices"]), sm, c["res_slice"], interp, True, True)
+    for eq in (0, 1):
+        v, vw = sa.adjoint_forward(tf, psf, cuda(c["slices"]), sm, vm, c["vol_shape"], c["res_slice"], interp, eq)
+        out[f"adj{eq}_vol"] = v
+        gs, gt = sa.adjoint_backward(tf, cuda(c["grad_vol"]).clone(), vw, vm, psf, cuda(c["slices"]), sm, v, c["res_slice"], interp, eq, True, True)
+        out[f"adjbwd{eq}_grad_slices"], out[f"adjbwd{eq}_grad_tf"] = gs, gt
+    return {k: v.cpu() for k, v in out.items()}
+
+
+def _tol(key):
+    if key in ("slices", "weight") or key.endswith("grad_slices"):
+        return GATHER_TOL
+    if key.endswith("grad_tf"):
+        return dict(atol=2e-3, rtol=2e-4)  # sums of O(1e2..1e4) terms reduced in a different order
+    return SCATTER_TOL
+
+
+@pytest.mark.parametrize("interp", [0, 1])
+@pytest.mark.parametrize("tag,kw", [("plain", dict(masks=False)), ("masked", dict(masks=True, seed=1))])
+def test_against_reference_kernel_outputs(native_lib, tag, kw, interp):
+    gold = np.load(os.path.join(GOLD, "slice_acq_ref.npz"))
+    got = _native_all(slice_acq_case(**kw), interp)
+    for k, v in got.items():
+        ref = torch.from_numpy(gold[f"{tag}_i{interp}_{k}"])
+        if k == "adjbwd1_grad_slices":  # gathers an equalized (scatter-produced) grad_vol: round-off, not bits
+            torch.testing.assert_close(v, ref, atol=2e-4, rtol=2e-4, msg=lambda m: f"{k}: {m}")
+        else:
+            torch.testing.assert_close(v, ref, **_tol(k), msg=lambda m: f"{k}: {m}")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_against_oracle_seeded(native_lib, oracle, dtype):
+    from test_oracle_slice_acq import _run_all
+
+    for interp in (0, 1):
+        c = slice_acq_case(seed=21, dtype=dtype, masks=True, D=33, H=29, W=31, n=7, h=37, w=35)
+        got, ref = _native_all(c, interp), _run_all(oracle, c, interp)
+        for k, v in got.items():
+            tol = _tol(k) if dtype == np.float32 else dict(atol=1e-10, rtol=1e-9)
+            if k == "adjbwd1_grad_slices" and dtype == np.float32:
+                tol = dict(atol=2e-4, rtol=2e-4)
+            torch.testing.assert_close(v, torch.from_numpy(ref[k]), **tol, msg=lambda m: f"{k} interp={interp}: {m}")
+
+
+def test_edge_cases(native_lib):
+    import nesvor_b200 as nb
+
+    c = slice_acq_case(n=2)
+    tf, vol, psf = cuda(c["transforms"]), cuda(c["vol"]), cuda(c["psf"])
+    empty = nb.slice_acquisition(tf[:0], vol, None, None, psf, c["slice_shape"], 1.5, False, False)
+    assert empty.shape == (0, 1) + c["slice_shape"]
+    none = torch.zeros(2, 1, *c["slice_shape"], dtype=torch.bool, device="cuda")
+    assert not nb.slice_acquisition(tf, vol, None, none, psf, c["slice_shape"], 1.5, False, False).any()
+    far = tf.clone()
+    far[:, :, 3] = 1e4
+    s, w = nb.slice_acquisition(far, vol, None, None, psf, c["slice_shape"], 1.5, True, False)
+    assert not s.any() and not w.any()
+    with pytest.raises(RuntimeError, match="contiguous"):
+        nb.slice_acquisition(tf, vol.transpose(-1, -2), None, None, psf, c["slice_shape"], 1.5, False, False)
+    # autograd wiring: gradients w.r.t. volume and transforms exist and match a finite difference in fp64
+    vol64 = vol.double().requires_grad_(True)
+    out = nb.slice_acquisition(tf.double(), vol64, None, None, psf.double(), c["slice_shape"], 1.5, False, False)
+    g = torch.randn_like(out)
+    (gv,) = torch.autograd.grad(out, vol64, g)
+    d = torch.randn_like(vol64)
+    eps = 1e-6
+    o2 = nb.slice_acquisition(tf.double(), (vol64 + eps * d).detach(), None, None, psf.double(), c["slice_shape"], 1.5, False, False)
+    np.testing.assert_allclose(float((gv * d).sum()), float(((o2 - out.detach()) * g).sum() / eps), rtol=1e-5)
+
+
+def _cg(A, b, x0, n_iter, tol):  # nesvor/svort/srr.py:12-34
+    x, r = x0, b - A(x0)
+    p, rr, i = r, torch.dot(r.flatten(), r.flatten()), 0
+    while True:
+        Ap = A(p)
+        alpha = rr / torch.dot(p.flatten(), Ap.flatten())
+        x = x + alpha * p
+        i += 1
+        if i == n_iter:
+            return x
+        r = r - alpha * Ap
+        rr_new = torch.dot(r.flatten(), r.flatten())
+        if rr_new <= tol:
+            return x
+        p = r + (rr_new / rr) * p
+        rr = rr_new
+
+
+def test_cg_recovers_phantom_known_answer(native_lib):
+    """The reference's only KAT for A / A^T (tests/slice_acquisition/test_slice_acq.py:76-81)."""
+    import nesvor_b200 as nb
+    from nesvor_b200.data.phantom import phantom3d, stack_axisangles, stack_geometry
+
+    vs, gap, res, res_s = 32, 3.0, 1.0, 1.5
+    ss, n_slice = stack_geometry(vs, res, res_s, gap)
+    volume = torch.tensor(phantom3d(vs), dtype=torch.float32).cuda()[None, None]
+    psf = nb.get_PSF(res_ratio=(res_s / res, res_s / res, gap / res)).cuda()
+    pi = np.pi
+    angles = [[0, 0, 0], [pi / 2, 0, 0], [0, pi / 2, 0], [0, 0, pi / 2], [pi / 4, pi / 4, 0], [0, pi / 4, pi / 4],
+              [pi / 4, 0, pi / 4], [pi / 3, pi / 3, 0], [0, pi / 3, pi / 3], [pi / 3, 0, pi / 3], [2 * pi / 3, 2 * pi / 3, 0],
+              [0, 2 * pi / 3, 2 * pi / 3], [2 * pi / 3, 0, 2 * pi / 3], [pi / 5, pi / 5, 0], [0, pi / 5, pi / 5], [pi / 5, 0, pi / 5]]
+    transform = nb.RigidTransform(stack_axisangles(angles, n_slice, gap).cuda(), trans_first=True)
+    theta = nb.mat_update_resolution(transform.matrix(), 1, res).contiguous()
+    A = lambda x: nb.slice_acquisition(theta, x, None, None, psf, (ss, ss), res_s / res, False, False)
+    At = lambda y: nb.slice_acquisition_adjoint(theta, psf, y, None, None, (vs, vs, vs), res_s / res, False, False)
+    slices = A(volume)
+    rec = torch.relu(_cg(lambda x: At(A(x)), At(slices), volume, 20, 1e-8))
+    torch.testing.assert_close(rec, volume, atol=3e-5, rtol=1e-5)
+
+
+def test_adjointness_at_baseline_size(native_lib):
+    """Size-independent property at the config-2 stack size (3 x 77 slices of 225^2 over 128^3):
+    <A x, y> == <x, A^T y> restricted to interior pixels (Q3/Q4 only differ at the border)."""
+    import nesvor_b200 as nb
+    from nesvor_b200.data.phantom import STACK_ORIENTATIONS, stack_axisangles, stack_geometry
+
+    n, res_s, gap = 128, 1.0, 3.0
+    ss, n_slice = stack_geometry(n, 1.0, res_s, gap)
+    assert (ss, n_slice) == (225, 77)
+    psf = nb.get_PSF(res_ratio=(1.0, 1.0, 3.0)).cuda().double()
+    theta = nb.axisangle2mat(stack_axisangles(STACK_ORIENTATIONS[:3], n_slice, gap).cuda()).double().contiguous()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand(1, 1, n, n, n, generator=g, device="cuda", dtype=torch.float64)
+    y = torch.rand(theta.shape[0], 1, ss, ss, generator=g, device="cuda", dtype=torch.float64)
+    Ax, w = nb.slice_acquisition(theta, x, None, None, psf, (ss, ss), 1.0, True, False)
+    interior = w > w.max() * (1 - 1e-9)  # full PSF support: A and A^T normalise identically
+    y = y * interior
+    Aty = nb.slice_acquisition_adjoint(theta, psf, y, None, None, (n, n, n), 1.0, False, False)
+    lhs, rhs = float((Ax * y).sum()), float((x * Aty).sum())
+    assert interior.float().mean() > 0.05
+    np.testing.assert_allclose(lhs, rhs, rtol=1e-9)

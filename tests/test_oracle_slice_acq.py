@@ -1,0 +1,150 @@
+"""CPU tests (no GPU): the C restatement of slice acquisition vs
+(a) golden outputs of the reference's own kernels (tests/golden/slice_acq_ref.npz),
+(b) oracle/_ref live, bit for bit, when available,
+(c) the reference's known-answer test: 20 CG iterations through A / A^T recover the 32^3
+    phantom from 16 simulated stacks (/root/reference/tests/slice_acquisition/test_slice_acq.py:13-81,
+    CG and SRR.A/At/AtA restated from nesvor/svort/srr.py:12-34,104-137),
+plus the golden PSF / phantom fixtures for the product's host-side generators."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import gaussian_psf, slice_acq_case
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _run_all(lib, c, interp):
+    out = {}
+    out["slices"], out["weight"] = lib.forward(c["transforms"], c["vol"], c["vol_mask"], c["slices_mask"], c["psf"], c["slice_shape"], c["res_slice"], True, interp)
+    out["bwd_grad_vol"], out["bwd_grad_tf"] = lib.backward(c["transforms"], c["vol"], c["vol_mask"], c["psf"], c["grad_slices"], c["slices_mask"], c["res_slice"], interp, True, True)
+    for eq in (0, 1):
+        vol, vw = lib.adjoint_forward(c["transforms"], c["psf"], c["slices"], c["slices_mask"], c["vol_mask"], c["vol_shape"], c["res_slice"], interp, eq)
+        out[f"adj{eq}_vol"] = vol
+        gs, gt = lib.adjoint_backward(c["transforms"], c["grad_vol"].copy(), vw, c["vol_mask"], c["psf"], c["slices"], c["slices_mask"], vol, c["res_slice"], interp, eq, True, True)
+        out[f"adjbwd{eq}_grad_slices"], out[f"adjbwd{eq}_grad_tf"] = gs, gt
+    return out
+
+
+@pytest.mark.parametrize("interp", [0, 1])
+@pytest.mark.parametrize("tag,kw", [("plain", dict(masks=False)), ("masked", dict(masks=True, seed=1))])
+def test_oracle_matches_reference_golden(oracle, tag, kw, interp):
+    from oracle import native
+
+    native.set_threads(1)
+    gold = np.load(os.path.join(GOLD, "slice_acq_ref.npz"))
+    got = _run_all(oracle, slice_acq_case(**kw), interp)
+    for k, v in got.items():
+        assert np.array_equal(v, gold[f"{tag}_i{interp}_{k}"]), k  # bit-exact, single thread
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_oracle_bit_exact_vs_live_reference(oracle, reference_cpu, dtype):
+    from oracle import native
+
+    native.set_threads(1)
+    for interp in (0, 1):
+        c = slice_acq_case(seed=11, dtype=dtype, masks=True, D=17, H=19, W=23, n=3, h=21, w=16)
+        a, b = _run_all(oracle, c, interp), _run_all(reference_cpu, c, interp)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (k, interp)
+
+
+def test_empty_and_fully_masked(oracle):
+    c = slice_acq_case(n=2)
+    none = np.zeros_like(c["slices"], dtype=bool)
+    s, w = oracle.forward(c["transforms"], c["vol"], None, none, c["psf"], c["slice_shape"], c["res_slice"], True, 0)
+    assert not s.any() and not w.any()
+    far = c["transforms"].copy()
+    far[:, :, 3] = 1e4  # every tap out of the volume -> weight 0 -> output stays 0 (Q1)
+    s, = oracle.forward(far, c["vol"], None, None, c["psf"], c["slice_shape"], c["res_slice"], False, 0)
+    assert not s.any()
+    s0 = oracle.forward(c["transforms"][:0], c["vol"], None, None, c["psf"], c["slice_shape"], c["res_slice"], False, 0)[0]
+    assert s0.shape[0] == 0
+
+
+def test_adjointness(oracle):
+    """<A x, y> == <x, A^T y> up to the border rules Q3/Q4 (pixels well inside the volume)."""
+    rng = np.random.default_rng(5)
+    D = H = W = 40
+    psf = gaussian_psf((1.0, 1.0, 3.0), np.float64)
+    n, h, w = 4, 12, 12
+    tf = np.zeros((n, 3, 4))
+    from helpers import rotvec_to_mat
+
+    for i in range(n):
+        tf[i, :, :3] = rotvec_to_mat(rng.normal(size=3) * 0.5)
+        tf[i, :, 3] = rng.normal(size=3)
+    x = rng.random((1, 1, D, H, W))
+    y = rng.random((n, 1, h, w))
+    # un-normalised operators: A normalises by the tap weight, A^T by the same (unmasked) weight
+    Ax, wgt = oracle.forward(tf, x, None, None, psf, (h, w), 1.0, True, 0)
+    Aty = oracle.adjoint_forward(tf, psf, y, None, None, (D, H, W), 1.0, 0, 0)[0]
+    assert abs(wgt.min() - wgt.max()) < 1e-9  # interior pixels: full PSF support
+    np.testing.assert_allclose((Ax * y).sum(), (x * Aty).sum(), rtol=1e-10)
+
+
+def _cg(A, b, x0, n_iter, tol):
+    x = x0
+    r = b - A(x)
+    p = r
+    rr = float((r * r).sum())
+    i = 0
+    while True:
+        Ap = A(p)
+        alpha = rr / float((p * Ap).sum())
+        x = x + alpha * p
+        i += 1
+        if i == n_iter:
+            return x
+        r = r - alpha * Ap
+        rr_new = float((r * r).sum())
+        if rr_new <= tol:
+            return x
+        p = r + (rr_new / rr) * p
+        rr = rr_new
+
+
+def test_cg_recovers_phantom_known_answer(oracle):
+    from oracle import native
+    from nesvor_b200.data.phantom import phantom3d, stack_axisangles, stack_geometry
+
+    native.set_threads(os.cpu_count() or 1)
+    vs, gap, res, res_s = 32, 3.0, 1.0, 1.5
+    ss, n_slice = stack_geometry(vs, res, res_s, gap)
+    assert (ss, n_slice) == (40, 22)
+    volume = phantom3d(vs).astype(np.float32)[None, None]
+    psf = gaussian_psf((res_s / res, res_s / res, gap / res))
+    assert psf.shape == (9, 5, 5) and int((psf != 0).sum()) == 153
+    pi = np.pi
+    angles = [[0, 0, 0], [pi / 2, 0, 0], [0, pi / 2, 0], [0, 0, pi / 2], [pi / 4, pi / 4, 0], [0, pi / 4, pi / 4],
+              [pi / 4, 0, pi / 4], [pi / 3, pi / 3, 0], [0, pi / 3, pi / 3], [pi / 3, 0, pi / 3], [2 * pi / 3, 2 * pi / 3, 0],
+              [0, 2 * pi / 3, 2 * pi / 3], [2 * pi / 3, 0, 2 * pi / 3], [pi / 5, pi / 5, 0], [0, pi / 5, pi / 5], [pi / 5, 0, pi / 5]]
+    ax = stack_axisangles(angles, n_slice, gap).numpy()
+    tf = oracle.axisangle2mat_forward(ax)[0]  # res_r = 1: mat_update_resolution is the identity
+    A = lambda x: oracle.forward(tf, x, None, None, psf, (ss, ss), res_s / res, False, 0)[0]
+    At = lambda y: oracle.adjoint_forward(tf, psf, y, None, None, (vs, vs, vs), res_s / res, 0, 0)[0]
+    slices = A(volume)
+    rec = _cg(lambda x: At(A(x)), At(slices), volume, 20, 1e-8)
+    rec = np.maximum(rec, 0)
+    torch.testing.assert_close(torch.from_numpy(rec), torch.from_numpy(volume), atol=3e-5, rtol=1e-5)
+    native.set_threads(1)
+
+
+def test_host_generators_match_reference_golden():
+    from nesvor_b200.data.phantom import phantom3d
+    from nesvor_b200.utils import psf as P
+
+    g = np.load(os.path.join(GOLD, "psf_ref.npz"))
+    assert np.allclose(g["constants"], [P.GAUSSIAN_FWHM, P.SINC_FWHM], rtol=0, atol=0)
+    for ratio in ((1.5, 1.5, 3.0), (1.25, 1.25, 3.75), (1.0, 1.0, 3.0), (1.0, 1.0, 1.0)):
+        ours = P.get_PSF(res_ratio=ratio).numpy()
+        assert np.array_equal(ours, g["psf_%g_%g_%g" % ratio])
+    ph = np.load(os.path.join(GOLD, "phantom_ref.npz"))
+    assert np.array_equal(phantom3d(16).astype(np.float32), ph["n16"])
+    assert np.array_equal(phantom3d(32).astype(np.float32), ph["n32"])
+    sha = hashlib.sha1(phantom3d(64).astype(np.float32).tobytes()).digest()
+    assert np.array_equal(np.frombuffer(sha, np.uint8), ph["sha1_n64"])
