@@ -187,9 +187,9 @@ typedef struct nsv_inr_grads {    /* device pointers, all fp32, caller zero-fill
   float* mlp;                     /* same layout as mlp_f16 (element for element) */
   float* axisangle;               /* [n_slices, 6] or NULL */
   float* slice_embedding;
-  float* slice_scale_c;           /* [n_slices]: dL/dc_k (softmax chain rule left to the caller) */
+  float* slice_scale_c;           /* [n_slices]: receives dL/dlogit_coef (softmax chain rule applied by the finalize kernel) */
   float* log_var_slice;
-  float* losses;                  /* [8]: MSE, logVar, biasReg(sum log_bias), imageReg, ... as partial sums */
+  float* losses;                  /* [8]: [0] MSE, [1] logVar, [2] biasReg, [3] imageReg (final values) */
 } nsv_inr_grads;
 
 /* number of fp16 elements of the packed MLP buffer and per-net offsets (host helper) */
@@ -211,9 +211,9 @@ int nsv_inr_render(const nsv_inr_config* h_cfg, const nsv_inr_params* h_params,
  * Replaces torch.optim.AdamW as configured in nesvor/nesvor/train.py:134-152 (+ GradScaler
  * unscale, train.py:162-164,195).
  * ------------------------------------------------------------------------------------------ */
-int nsv_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_f16 /* or NULL */,
+int nsv_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* param_f16 /* or NULL */,
                    int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                   float grad_unscale, void* stream);
+                   float grad_unscale, int zero_grad /* clear grad for the next iteration */, void* stream);
 
 #ifdef __cplusplus
 }

@@ -190,14 +190,15 @@ extern "C" int64_t nsv_grid_meta_init(nsv_grid_meta* m, int n_levels, int n_feat
   }
   m->n_levels = n_levels;
   m->n_features = n_features;
-  const float log2s = log2f(per_level_scale);
+  // double precision, narrowed once: the float libm entry points differ in the last bit between hosts
+  const double log2s = log2((double)per_level_scale);
   uint64_t off = 0;
   for (int l = 0; l < NSV_MAX_LEVELS; ++l) {
     if (l >= n_levels) {
       m->scale[l] = 0.f; m->res[l] = 0; m->size[l] = 0; m->hashed[l] = 0; m->offset[l + 1] = (uint32_t)off;
       continue;
     }
-    const float scale = exp2f((float)l * log2s) * (float)base_resolution - 1.0f;
+    const float scale = (float)(exp2((double)l * log2s) * (double)base_resolution - 1.0);
     const uint32_t res = (uint32_t)ceilf(scale) + 1u;
     const uint64_t cube = (uint64_t)res * res * res;
     uint64_t dense = cube > 0x7fffffffull ? 0x7fffffffull : cube;

@@ -1,0 +1,889 @@
+// inr_fused.cu -- kernel A: one fused NeSVoR training iteration (and the forward-only renderer).
+//
+// Replaces, in ONE launch, the per-iteration op sequence of the reference
+//   NeSVoR.forward -> ax_transform_points -> INR.forward (tcnn HashGrid + tcnn MLP) -> sigma_net ->
+//   render / losses / edge regulariser -> autograd backward (MLP bwd, hash-grid scatter, pose VJP)
+// (nesvor/nesvor/models.py:260-384, driven by nesvor/nesvor/train.py:183-190), which the reference
+// executes as ~100 launches with every [N, *] intermediate round-tripping HBM.
+//
+// Organisation (sm_100a, persistent: one 256-thread CTA per SM, 8 warps):
+//   * a CTA tile = 256 PSF samples = 256/S whole pixels, so the per-pixel mean over S samples and
+//     the sample <-> S-1-sample pairing of the image regulariser stay inside the CTA;
+//   * phase 0 (thread = sample): pose (Rodrigues in registers), x = R(p + sigma*eps + T), bbox
+//     normalisation, L-level hash-grid gather from the fp16 table (L2-resident), trilinear blend in
+//     fp32, features parked as fp16 in the CTA's shared tile (the only copy ever made);
+//   * phase 1 (warp = 32 samples): density MLP (and sigma MLP) on tensor-core fragments with all
+//     weights in shared memory, activations in registers (mlp_mma.cuh);
+//   * phase 2 (thread = sample): softplus, per-pixel means, slice scale / variance, losses and their
+//     analytic gradients;
+//   * phase 3: MLP dgrad/wgrad on fragments (weight gradients live in registers across tiles and
+//     are flushed once per CTA), then per-sample scatter of dL/d(features) into the fp32 table
+//     gradient with vector reductions (red.global.add.v2.f32), and -- when poses are optimised --
+//     dL/dx through the grid, reduced per pixel and pushed through the Rodrigues VJP.
+// Nothing but the table gradient, O(weights) and O(slices) values is written to global memory.
+#include "hashgrid.cuh"
+#include "mlp_mma.cuh"
+#include "pose.cuh"
+
+namespace nsv {
+namespace {
+
+constexpr int kTile = 256, kNW = 8, kIn = 32, kOutP = 16;
+constexpr int kLddx = kIn + 1;
+
+struct FusedArgs {
+  nsv_inr_config cfg;
+  const __half* table;
+  const __half* mlp;
+  const float* axisangle;
+  const float* psf_sigma;
+  const float* slice_embedding;
+  const float* logit_coef;
+  const float* log_var_slice;
+  int n_slices;
+  float* g_table;
+  float* g_mlp;
+  float* g_axisangle;
+  float* g_se;
+  float* g_c;
+  float* g_lvs;
+  float* losses;
+  const float* xyz;
+  const float* v;
+  const int64_t* slice_idx;
+  const float* noise;
+  uint64_t seed, offset;
+  float* v_out;
+  int64_t B;
+  int S, log2S;
+  int64_t off_density, off_sigma;
+};
+
+template <int W, int DEPTH, bool SIGMA>
+struct Layout {
+  static constexpr int ldx = kIn + kPad, ldh = W + kPad, ldg = kOutP + kPad;
+  // fp16 region (offsets in halves)
+  static constexpr size_t wd0 = 0;
+  static constexpr size_t wdh = wd0 + (size_t)W * ldx;
+  static constexpr size_t wdo = wdh + (size_t)(DEPTH - 1) * W * ldh;
+  static constexpr size_t ws0 = wdo + (size_t)kOutP * ldh;
+  static constexpr size_t wso = ws0 + (SIGMA ? (size_t)W * ldx : 0);
+  static constexpr size_t sx = wso + (SIGMA ? (size_t)kOutP * ldh : 0);
+  static constexpr size_t sh = sx + (size_t)kTile * ldx;
+  static constexpr size_t sg = sh + (size_t)DEPTH * kTile * ldh;
+  static constexpr size_t ssx = sg + (size_t)kTile * ldg;
+  static constexpr size_t ssh = ssx + (SIGMA ? (size_t)kTile * ldx : 0);
+  static constexpr size_t halves = ssh + (SIGMA ? (size_t)kTile * ldh : 0);
+  static constexpr size_t f_base = (halves * 2 + 15) / 16 * 16;  // bytes
+  // fp32 region (offsets in floats)
+  static constexpr size_t fdx = 0;                                // [256][33] dL/d(features)
+  static constexpr size_t fz0 = fdx + (size_t)kTile * kLddx;      // z0 / later dz0
+  static constexpr size_t flv = fz0 + kTile;                      // log_var / later dlv
+  static constexpr size_t frho = flv + kTile;
+  static constexpr size_t fxw = frho + kTile;                     // [256][3]
+  static constexpr size_t fred = fxw + 3 * kTile;                 // [8][16] warp partials
+  static constexpr size_t floats = fred + kNW * 16;
+  static constexpr size_t bytes = f_base + floats * 4;
+};
+
+// ---- Philox4x32-10 + Box-Muller: three N(0,1) per (seed, sample index) ----
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ void normal3(uint64_t seed, uint64_t idx, float e[3]) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float u0 = ((float)r.x + 0.5f) * 2.3283064365386963e-10f, u1 = ((float)r.y + 0.5f) * 2.3283064365386963e-10f;
+  const float u2 = ((float)r.z + 0.5f) * 2.3283064365386963e-10f, u3 = ((float)r.w + 0.5f) * 2.3283064365386963e-10f;
+  const float r0 = sqrtf(-2.f * __logf(u0)), r1 = sqrtf(-2.f * __logf(u2));
+  float s, c;
+  __sincosf(6.283185307179586f * u1, &s, &c);
+  e[0] = r0 * c;
+  e[1] = r0 * s;
+  e[2] = r1 * __cosf(6.283185307179586f * u3);
+}
+
+// ---- phase 0: encode one sample into its fp16 row of the shared tile ----
+__device__ __forceinline__ void encode_row(const float xn[3], const nsv_grid_meta& m, const __half* __restrict__ table, __half* row) {
+#pragma unroll 2
+  for (int l = 0; l < m.n_levels; ++l) {
+    const LevelGeom lv = level_geom(m, l);
+    uint32_t g[3];
+    float w[3];
+    level_pos(xn, lv.scale, g, w);
+    float2 f[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      f[c] = load_pair(table, lv.offset + vertex_index(lv, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2)));
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float wt = corner_weight(c, w);
+      a0 = fmaf(wt, f[c].x, a0);
+      a1 = fmaf(wt, f[c].y, a1);
+    }
+    *reinterpret_cast<__half2*>(row + 2 * l) = __floats2half2_rn(a0, a1);
+  }
+  for (int l = m.n_levels; l < kIn / 2; ++l) *reinterpret_cast<uint32_t*>(row + 2 * l) = 0u;
+}
+
+// ---- phase 3 tail: scatter dL/d(features) of one sample; optionally dL/dx through the grid ----
+template <bool kInputGrad>
+__device__ __forceinline__ void scatter_row(const float xn[3], const nsv_grid_meta& m, const __half* __restrict__ table,
+                                            const float* grow, float inv_scale, float* __restrict__ g_table, float gx[3]) {
+  if (kInputGrad) gx[0] = gx[1] = gx[2] = 0.f;
+#pragma unroll 2
+  for (int l = 0; l < m.n_levels; ++l) {
+    const float g0 = grow[2 * l] * inv_scale, g1 = grow[2 * l + 1] * inv_scale;
+    const LevelGeom lv = level_geom(m, l);
+    uint32_t g[3];
+    float w[3];
+    level_pos(xn, lv.scale, g, w);
+    uint32_t e[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) e[c] = lv.offset + vertex_index(lv, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2));
+    if (kInputGrad) {
+      float2 f[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) f[c] = load_pair(table, e[c]);
+      float d[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float dot = fmaf(f[c].x, g0, f[c].y * g1);
+        const float fx = (c & 1) ? w[0] : 1.f - w[0], fy = (c & 2) ? w[1] : 1.f - w[1], fz = (c & 4) ? w[2] : 1.f - w[2];
+        d[0] += ((c & 1) ? dot : -dot) * fy * fz;
+        d[1] += ((c & 2) ? dot : -dot) * fx * fz;
+        d[2] += ((c & 4) ? dot : -dot) * fx * fy;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) gx[k] = fmaf(lv.scale, d[k], gx[k]);
+    }
+    if (g0 != 0.f || g1 != 0.f) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float wt = corner_weight(c, w);
+        red_add_v2(g_table + 2 * (size_t)e[c], wt * g0, wt * g1);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float softplus_f(float z) { return z > 20.f ? z : log1pf(expf(z)); }
+__device__ __forceinline__ float sigmoid_f(float z) { return 1.f / (1.f + expf(-z)); }
+
+// column 0 of a 2-n-tile accumulator -> per-row scalar array (rows of this warp)
+__device__ __forceinline__ void store_col0(const float (&c)[2][2][4], float* dst, int row0) {
+  const int lane = threadIdx.x & 31;
+  if ((lane & 3) == 0) {
+    const int g = lane >> 2;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      dst[row0 + m * 16 + g] = c[m][0][0];
+      dst[row0 + m * 16 + g + 8] = c[m][0][2];
+    }
+  }
+}
+
+template <int W, int DEPTH, bool SIGMA>
+__global__ void __launch_bounds__(kTile, 1) inr_train_kernel(const __grid_constant__ FusedArgs a) {
+  using L = Layout<W, DEPTH, SIGMA>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __half* sh = reinterpret_cast<__half*>(smem_raw);
+  float* sf = reinterpret_cast<float*>(smem_raw + L::f_base);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row0 = warp * 32;
+  const nsv_inr_config& cfg = a.cfg;
+
+  // ---- stage weights (fp16, padded rows) ----
+  {
+    const __half* wd = a.mlp + a.off_density;
+    stage_weights(sh + L::wd0, L::ldx, wd, W, kIn);
+    for (int l = 0; l + 1 < DEPTH; ++l) stage_weights(sh + L::wdh + (size_t)l * W * L::ldh, L::ldh, wd + (size_t)W * kIn + (size_t)l * W * W, W, W);
+    stage_weights(sh + L::wdo, L::ldh, wd + (size_t)W * kIn + (size_t)(DEPTH - 1) * W * W, kOutP, W);
+    if (SIGMA) {
+      const __half* ws = a.mlp + a.off_sigma;
+      stage_weights(sh + L::ws0, L::ldx, ws, W, kIn);
+      stage_weights(sh + L::wso, L::ldh, ws + (size_t)W * kIn, kOutP, W);
+    }
+  }
+  // ---- log-sum-exp of logit_coef (slice scale c_k = n_s softmax_k) ----
+  float lse = 0.f;
+  if (cfg.slice_scale) {
+    float mx = -INFINITY;
+    for (int k = tid; k < a.n_slices; k += kTile) mx = fmaxf(mx, a.logit_coef[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) sf[L::fred + warp] = mx;
+    __syncthreads();
+    mx = sf[L::fred];
+    for (int k = 1; k < kNW; ++k) mx = fmaxf(mx, sf[L::fred + k]);
+    __syncthreads();
+    float se = 0.f;
+    for (int k = tid; k < a.n_slices; k += kTile) se += expf(a.logit_coef[k] - mx);
+    se = warp_sum(se);
+    if (lane == 0) sf[L::fred + warp] = se;
+    __syncthreads();
+    se = 0.f;
+    for (int k = 0; k < kNW; ++k) se += sf[L::fred + k];
+    lse = mx + logf(se);
+  }
+  __syncthreads();
+
+  // weight-gradient accumulators (registers, persistent across tiles)
+  float acc_d0[WgradSplit<W, kIn, kNW>::NTW][4] = {};
+  float acc_dh[DEPTH > 1 ? DEPTH - 1 : 1][WgradSplit<W, W, kNW>::NTW][4] = {};
+  float acc_do[WgradSplit<kOutP, W, kNW>::NTW][4] = {};
+  float acc_s0[WgradSplit<W, kIn, kNW>::NTW][4] = {};
+  float acc_so[WgradSplit<kOutP, W, kNW>::NTW][4] = {};
+  float loss_d = 0.f, loss_s = 0.f, loss_i = 0.f;
+
+  const int S = a.S, wpp = S >> 5;  // warps per pixel
+  const float invS = 1.f / (float)S, invB = 1.f / (float)a.B, gscale = cfg.grad_scale, inv_gscale = 1.f / cfg.grad_scale;
+  const int64_t n_tiles = (a.B * (int64_t)S) / kTile;
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    __syncthreads();  // previous tile's cooperative wgrad reads are complete
+    // ================= phase 0: sample geometry + encoding =================
+    const int64_t sidx = tile * kTile + tid;
+    const int64_t p = sidx >> a.log2S;
+    const int j = (int)(sidx & (S - 1));
+    const int k = (int)a.slice_idx[p];
+    float ax[6], R[9], y[3], xw[3], xn[3];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) ax[d] = a.axisangle[(size_t)k * 6 + d];
+    rodrigues<float>(ax, R);
+    {
+      float eps[3];
+      if (a.noise) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) eps[d] = a.noise[sidx * 3 + d];
+      } else {
+        normal3(a.seed, a.offset + (uint64_t)sidx, eps);
+      }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) y[d] = (a.xyz[p * 3 + d] + eps[d] * a.psf_sigma[(size_t)k * 3 + d]) + ax[3 + d];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        xw[i] = R[i * 3] * y[0] + R[i * 3 + 1] * y[1] + R[i * 3 + 2] * y[2];
+        xn[i] = (xw[i] - cfg.bbox_lo[i]) / (cfg.bbox_hi[i] - cfg.bbox_lo[i]);
+      }
+    }
+    encode_row(xn, cfg.grid, a.table, sh + L::sx + (size_t)tid * L::ldx);
+    __syncwarp();
+
+    // ================= phase 1: density MLP forward (warp-local) =================
+    uint32_t az[2][1][4];  // z0..z15 as an A fragment (input of sigma_net)
+    {
+      uint32_t ain[2][kIn / 16][4];
+      load_a_frags<kIn / 16>(ain, sh + L::sx, L::ldx, row0);
+      float c[2][W / 8][4];
+      warp_gemm_fwd<kIn / 16, W / 8>(c, ain, sh + L::wd0, L::ldx);
+      uint32_t ah[2][W / 16][4];
+      acc_to_a<W / 8, true>(ah, c);
+      store_a_frags<W / 16>(ah, sh + L::sh, L::ldh, row0);
+#pragma unroll
+      for (int l = 1; l < DEPTH; ++l) {
+        warp_gemm_fwd<W / 16, W / 8>(c, ah, sh + L::wdh + (size_t)(l - 1) * W * L::ldh, L::ldh);
+        acc_to_a<W / 8, true>(ah, c);
+        store_a_frags<W / 16>(ah, sh + L::sh + (size_t)l * kTile * L::ldh, L::ldh, row0);
+      }
+      float co[2][2][4];
+      warp_gemm_fwd<W / 16, 2>(co, ah, sh + L::wdo, L::ldh);
+      store_col0(co, sf + L::fz0, row0);
+      acc_to_a<2, false>(az, co);
+    }
+    // ================= phase 1b: sigma MLP forward =================
+    if (SIGMA) {
+      __half* srow = sh + L::ssx + (size_t)tid * L::ldx;  // [slice embedding (16) | z (16)]
+      const float* se = a.slice_embedding + (size_t)k * 16;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) *reinterpret_cast<__half2*>(srow + 2 * q) = __floats2half2_rn(se[2 * q], se[2 * q + 1]);
+      store_a_frags<1>(az, sh + L::ssx + 16, L::ldx, row0);
+      __syncwarp();
+      uint32_t asx[2][2][4];
+      load_a_frags<2>(asx, sh + L::ssx, L::ldx, row0);
+      float c[2][W / 8][4];
+      warp_gemm_fwd<2, W / 8>(c, asx, sh + L::ws0, L::ldx);
+      uint32_t ash[2][W / 16][4];
+      acc_to_a<W / 8, true>(ash, c);
+      store_a_frags<W / 16>(ash, sh + L::ssh, L::ldh, row0);
+      float co[2][2][4];
+      warp_gemm_fwd<W / 16, 2>(co, ash, sh + L::wso, L::ldh);
+      store_col0(co, sf + L::flv, row0);
+    }
+    __syncwarp();
+
+    // ================= phase 2: render, losses, gradients w.r.t. z0 / log_var =================
+    const float z0 = sf[L::fz0 + tid];
+    const float rho = softplus_f(z0);
+    const float lv = SIGMA ? sf[L::flv + tid] : 0.f;
+    const float u = SIGMA ? expf(lv) : 1.f;
+    sf[L::frho + tid] = rho;
+    sf[L::fxw + 3 * tid] = xw[0];
+    sf[L::fxw + 3 * tid + 1] = xw[1];
+    sf[L::fxw + 3 * tid + 2] = xw[2];
+    {
+      const float s_rho = warp_sum(rho), s_u = warp_sum(u);
+      if (lane == 0) {
+        sf[L::fred + warp * 2] = s_rho;
+        sf[L::fred + warp * 2 + 1] = s_u;
+      }
+    }
+    __syncthreads();
+    float m_pix = 0.f, q_pix = 0.f;
+    {
+      const int w0 = (warp / wpp) * wpp;
+      for (int q = 0; q < wpp; ++q) {
+        m_pix += sf[L::fred + (w0 + q) * 2];
+        q_pix += sf[L::fred + (w0 + q) * 2 + 1];
+      }
+      m_pix *= invS;
+      q_pix *= invS;
+    }
+    const float ck = cfg.slice_scale ? (float)a.n_slices * expf(a.logit_coef[k] - lse) : 1.f;
+    const float vhat = ck * m_pix;
+    const float r = ck * q_pix;
+    float var = SIGMA ? r * r : 1.f;
+    const float evs = cfg.slice_variance ? expf(a.log_var_slice[k]) : 0.f;
+    var += evs;
+    const float e = vhat - a.v[p];
+    const float d_vhat = e / var * invB;
+    const float d_var = (SIGMA || cfg.slice_variance) ? (0.5f / var - 0.5f * e * e / (var * var)) * invB : 0.f;
+    float d_rho = ck * d_vhat * invS;
+    const float d_lv = SIGMA ? (u * invS) * ck * 2.f * r * d_var : 0.f;
+    if (j == 0) {
+      loss_d += 0.5f * e * e / var * invB;
+      if (SIGMA || cfg.slice_variance) loss_s += 0.5f * logf(var) * invB;
+      if (a.v_out) a.v_out[p] = vhat;
+      if (cfg.slice_scale) red_add(a.g_c + k, m_pix * d_vhat);
+      if (cfg.slice_variance) red_add(a.g_lvs + k, evs * d_var);
+    }
+    if (cfg.image_reg) {
+      const int tp = (tid & ~(S - 1)) + (S - 1 - j);
+      const float dr = rho - sf[L::frho + tp];
+      const float dx0 = xw[0] - sf[L::fxw + 3 * tp], dx1 = xw[1] - sf[L::fxw + 3 * tp + 1], dx2 = xw[2] - sf[L::fxw + 3 * tp + 2];
+      const float d2 = dx0 * dx0 + dx1 * dx1 + dx2 * dx2 + 1e-6f;
+      const float nbs = invB * invS;
+      if (cfg.image_reg == 2) {  // edge
+        const float sq = sqrtf(1.f + dr * dr / (d2 * cfg.delta * cfg.delta));
+        loss_i += sq * nbs;
+        d_rho += cfg.w_image * 2.f * dr / (cfg.delta * d2 * sq) * nbs;
+      } else if (cfg.image_reg == 1) {  // TV
+        const float dd = sqrtf(d2);
+        loss_i += fabsf(dr) / dd * nbs;
+        d_rho += cfg.w_image * 2.f * (dr > 0.f ? 1.f : (dr < 0.f ? -1.f : 0.f)) / dd * nbs;
+      } else {  // L2
+        loss_i += dr * dr / d2 * nbs;
+        d_rho += cfg.w_image * 4.f * dr / d2 * nbs;
+      }
+    }
+    const float dz0 = (z0 > 20.f ? 1.f : sigmoid_f(z0)) * d_rho * gscale;
+    sf[L::fz0 + tid] = dz0;  // own slot: z0 is dead
+    if (SIGMA) {
+      __half* grow = sh + L::sg + (size_t)tid * L::ldg;
+      *reinterpret_cast<uint4*>(grow) = make_uint4((uint32_t)__half_as_ushort(__float2half_rn(d_lv * gscale)), 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(grow + 8) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();  // [B0] sG / activations of every warp are in place
+
+    // ================= phase 3: backward =================
+    float c2[2][2][4];  // dL/dz (16 columns) of the density net, fp32 fragment
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c2[m][n][q] = 0.f;
+    if (SIGMA) {
+      warp_wgrad<kOutP, W, kNW>(acc_so, sh + L::sg, L::ldg, sh + L::ssh, L::ldh, kTile);
+      uint32_t ag[2][1][4];
+      load_a_frags<1>(ag, sh + L::sg, L::ldg, row0);
+      float c[2][W / 8][4];
+      warp_gemm_dgrad<1, W / 8>(c, ag, sh + L::wso, L::ldh);
+      relu_mask_acc<W / 8>(c, sh + L::ssh, L::ldh, row0);
+      uint32_t adz[2][W / 16][4];
+      acc_to_a<W / 8, false>(adz, c);
+      __syncthreads();  // [B1]
+      store_a_frags<W / 16>(adz, sh + L::ssh, L::ldh, row0);
+      __syncthreads();  // [B2]
+      warp_wgrad<W, kIn, kNW>(acc_s0, sh + L::ssh, L::ldh, sh + L::ssx, L::ldx, kTile);
+      float cin[2][4][4];
+      warp_gemm_dgrad<W / 16, 4>(cin, adz, sh + L::ws0, L::ldx);
+      // d(slice embedding): column sums over the warp's 32 rows (one pixel, one slice per warp)
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        float s0 = cin[0][n][0] + cin[0][n][2] + cin[1][n][0] + cin[1][n][2];
+        float s1 = cin[0][n][1] + cin[0][n][3] + cin[1][n][1] + cin[1][n][3];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        if (lane < 4) red_add_v2(a.g_se + (size_t)k * 16 + n * 8 + 2 * lane, s0 * inv_gscale, s1 * inv_gscale);
+      }
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) c2[m][n][q] = cin[m][2 + n][q];
+    }
+    if ((lane & 3) == 0) {  // add dL/dz0 of the render path to column 0
+      const int g = lane >> 2;
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        c2[m][0][0] += sf[L::fz0 + row0 + m * 16 + g];
+        c2[m][0][2] += sf[L::fz0 + row0 + m * 16 + g + 8];
+      }
+    }
+    uint32_t adz[2][W / 16][4];
+    {
+      uint32_t ag[2][1][4];
+      acc_to_a<2, false>(ag, c2);
+      store_a_frags<1>(ag, sh + L::sg, L::ldg, row0);  // sG is free: sigma's wgrad finished before [B1]
+      __syncthreads();  // [B3]
+      __half* sHl = sh + L::sh + (size_t)(DEPTH - 1) * kTile * L::ldh;
+      warp_wgrad<kOutP, W, kNW>(acc_do, sh + L::sg, L::ldg, sHl, L::ldh, kTile);
+      float c[2][W / 8][4];
+      warp_gemm_dgrad<1, W / 8>(c, ag, sh + L::wdo, L::ldh);
+      relu_mask_acc<W / 8>(c, sHl, L::ldh, row0);
+      acc_to_a<W / 8, false>(adz, c);
+      __syncthreads();  // [B4]
+      store_a_frags<W / 16>(adz, sHl, L::ldh, row0);
+      __syncthreads();  // [B5]
+    }
+#pragma unroll
+    for (int l = DEPTH - 1; l >= 1; --l) {
+      __half* sDz = sh + L::sh + (size_t)l * kTile * L::ldh;
+      __half* sHp = sh + L::sh + (size_t)(l - 1) * kTile * L::ldh;
+      warp_wgrad<W, W, kNW>(acc_dh[l - 1], sDz, L::ldh, sHp, L::ldh, kTile);
+      float c[2][W / 8][4];
+      warp_gemm_dgrad<W / 16, W / 8>(c, adz, sh + L::wdh + (size_t)(l - 1) * W * L::ldh, L::ldh);
+      relu_mask_acc<W / 8>(c, sHp, L::ldh, row0);
+      acc_to_a<W / 8, false>(adz, c);
+      __syncthreads();
+      store_a_frags<W / 16>(adz, sHp, L::ldh, row0);
+      __syncthreads();
+    }
+    warp_wgrad<W, kIn, kNW>(acc_d0, sh + L::sh, L::ldh, sh + L::sx, L::ldx, kTile);
+    {
+      float cx[2][kIn / 8][4];
+      warp_gemm_dgrad<W / 16, kIn / 8>(cx, adz, sh + L::wd0, L::ldx);
+      const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < kIn / 8; ++n) {
+          float* d0 = sf + L::fdx + (size_t)(row0 + m * 16 + g) * kLddx + n * 8 + 2 * t;
+          d0[0] = cx[m][n][0];
+          d0[1] = cx[m][n][1];
+          d0[8 * kLddx] = cx[m][n][2];
+          d0[8 * kLddx + 1] = cx[m][n][3];
+        }
+    }
+    __syncwarp();
+    // ---- per-sample scatter into the table gradient (+ pose gradient) ----
+    const float* grow = sf + L::fdx + (size_t)tid * kLddx;
+    if (cfg.pose_grad) {
+      float gx[3];
+      scatter_row<true>(xn, cfg.grid, a.table, grow, inv_gscale, a.g_table, gx);
+      float gw[3], part[12];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) gw[i] = gx[i] / (cfg.bbox_hi[i] - cfg.bbox_lo[i]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) part[i * 3 + q] = gw[i] * y[q];  // dL/dR
+#pragma unroll
+      for (int q = 0; q < 3; ++q) part[9 + q] = R[q] * gw[0] + R[3 + q] * gw[1] + R[6 + q] * gw[2];  // dL/dT = R^T g
+#pragma unroll
+      for (int q = 0; q < 12; ++q) part[q] = warp_sum(part[q]);
+      __syncthreads();  // fred is free again (phase-2 reads are long done), and all warps arrive here
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 12; ++q) sf[L::fred + warp * 16 + q] = part[q];
+      }
+      __syncthreads();
+      if (j == 0) {
+        float G[9], gT[3], gwv[3];
+        const int w0 = warp;  // first warp of this pixel
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+          float s = 0.f;
+          for (int ww = 0; ww < wpp; ++ww) s += sf[L::fred + (w0 + ww) * 16 + q];
+          if (q < 9) G[q] = s; else gT[q - 9] = s;
+        }
+        rodrigues_vjp<float>(ax, G, gwv);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          red_add(a.g_axisangle + (size_t)k * 6 + q, gwv[q]);
+          red_add(a.g_axisangle + (size_t)k * 6 + 3 + q, gT[q]);
+        }
+      }
+    } else {
+      float gx[3];
+      scatter_row<false>(xn, cfg.grid, a.table, grow, inv_gscale, a.g_table, gx);
+    }
+  }
+
+  // ================= epilogue: flush weight gradients and losses =================
+  {
+    float* gd = a.g_mlp + a.off_density;
+    flush_wgrad<W, kIn, kNW>(acc_d0, gd, kIn, inv_gscale);
+#pragma unroll
+    for (int l = 0; l + 1 < DEPTH; ++l) flush_wgrad<W, W, kNW>(acc_dh[l], gd + (size_t)W * kIn + (size_t)l * W * W, W, inv_gscale);
+    flush_wgrad<kOutP, W, kNW>(acc_do, gd + (size_t)W * kIn + (size_t)(DEPTH - 1) * W * W, W, inv_gscale);
+    if (SIGMA) {
+      float* gs = a.g_mlp + a.off_sigma;
+      flush_wgrad<W, kIn, kNW>(acc_s0, gs, kIn, inv_gscale);
+      flush_wgrad<kOutP, W, kNW>(acc_so, gs + (size_t)W * kIn, W, inv_gscale);
+    }
+  }
+  __syncthreads();
+  loss_d = warp_sum(loss_d);
+  loss_s = warp_sum(loss_s);
+  loss_i = warp_sum(loss_i);
+  if (lane == 0) {
+    red_add(a.losses + 0, loss_d);
+    red_add(a.losses + 1, loss_s);
+    red_add(a.losses + 3, loss_i);
+  }
+}
+
+// softmax chain rule for the slice scale + final loss values (1 block)
+__global__ void __launch_bounds__(256) inr_finalize_kernel(const float* __restrict__ logit_coef, float* __restrict__ g_c,
+                                                           float* __restrict__ losses, int n_slices, int slice_scale, int image_reg,
+                                                           float delta) {
+  __shared__ float red[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (slice_scale) {
+    float mx = -INFINITY;
+    for (int k = tid; k < n_slices; k += 256) mx = fmaxf(mx, logit_coef[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int k = 1; k < 8; ++k) mx = fmaxf(mx, red[k]);
+    __syncthreads();
+    float se = 0.f;
+    for (int k = tid; k < n_slices; k += 256) se += expf(logit_coef[k] - mx);
+    se = warp_sum(se);
+    if (lane == 0) red[warp] = se;
+    __syncthreads();
+    se = 0.f;
+    for (int k = 0; k < 8; ++k) se += red[k];
+    __syncthreads();
+    const float lse = mx + logf(se);
+    float dot = 0.f;  // sum_k gc_k c_k
+    for (int k = tid; k < n_slices; k += 256) dot += g_c[k] * (float)n_slices * expf(logit_coef[k] - lse);
+    dot = warp_sum(dot);
+    if (lane == 0) red[warp] = dot;
+    __syncthreads();
+    dot = 0.f;
+    for (int k = 0; k < 8; ++k) dot += red[k];
+    for (int k = tid; k < n_slices; k += 256) {
+      const float c = (float)n_slices * expf(logit_coef[k] - lse);
+      g_c[k] = c * (g_c[k] - dot / (float)n_slices);  // in place: dL/dlogit_k
+    }
+  }
+  if (tid == 0 && image_reg == 2) losses[3] = delta * (losses[3] - 1.f);
+}
+
+// ------------------------------------------------------------------------------------- renderer
+struct RenderArgs {
+  nsv_inr_config cfg;
+  const __half* table;
+  const __half* mlp;
+  int64_t off_density;
+  const float* xyz;
+  const float* mat;
+  int mat_per_point;
+  const float* psf_sigma;
+  int sigma_per_point;
+  const float* noise;
+  uint64_t seed, offset;
+  float* out;
+  int64_t M;
+  int S;
+};
+
+template <int W, int DEPTH>
+__global__ void __launch_bounds__(kTile, 1) inr_render_kernel(const __grid_constant__ RenderArgs a) {
+  using L = Layout<W, DEPTH, false>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __half* sh = reinterpret_cast<__half*>(smem_raw);
+  float* sf = reinterpret_cast<float*>(smem_raw + L::f_base);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row0 = warp * 32;
+  const nsv_inr_config& cfg = a.cfg;
+  const __half* wd = a.mlp + a.off_density;
+  stage_weights(sh + L::wd0, L::ldx, wd, W, kIn);
+  for (int l = 0; l + 1 < DEPTH; ++l) stage_weights(sh + L::wdh + (size_t)l * W * L::ldh, L::ldh, wd + (size_t)W * kIn + (size_t)l * W * W, W, W);
+  stage_weights(sh + L::wdo, L::ldh, wd + (size_t)W * kIn + (size_t)(DEPTH - 1) * W * W, kOutP, W);
+  __syncthreads();
+  const int64_t total = a.M * (int64_t)a.S;
+  const int64_t n_tiles = (total + kTile - 1) / kTile;
+  const float invS = 1.f / (float)a.S;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t sidx = tile * kTile + tid;
+    const bool valid = sidx < total;
+    const int64_t p = valid ? sidx / a.S : 0;
+    float xn[3] = {0.f, 0.f, 0.f};
+    if (valid) {
+      float y[3];
+      float eps[3] = {0.f, 0.f, 0.f};
+      if (a.S > 1 || a.noise) {
+        if (a.noise) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) eps[d] = a.noise[sidx * 3 + d];
+        } else {
+          normal3(a.seed, a.offset + (uint64_t)sidx, eps);
+        }
+      }
+      const float* sg = a.psf_sigma + (a.sigma_per_point ? p * 3 : 0);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) y[d] = a.xyz[p * 3 + d] + eps[d] * sg[d];
+      float xw[3] = {y[0], y[1], y[2]};
+      if (a.mat) {
+        const float* mt = a.mat + (a.mat_per_point ? p * 12 : 0);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) xw[i] = mt[i * 4] * (y[0] + mt[3]) + mt[i * 4 + 1] * (y[1] + mt[7]) + mt[i * 4 + 2] * (y[2] + mt[11]);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) xn[i] = (xw[i] - cfg.bbox_lo[i]) / (cfg.bbox_hi[i] - cfg.bbox_lo[i]);
+    }
+    encode_row(xn, cfg.grid, a.table, sh + L::sx + (size_t)tid * L::ldx);
+    __syncwarp();
+    uint32_t ain[2][kIn / 16][4];
+    load_a_frags<kIn / 16>(ain, sh + L::sx, L::ldx, row0);
+    float c[2][W / 8][4];
+    warp_gemm_fwd<kIn / 16, W / 8>(c, ain, sh + L::wd0, L::ldx);
+    uint32_t ah[2][W / 16][4];
+    acc_to_a<W / 8, true>(ah, c);
+#pragma unroll
+    for (int l = 1; l < DEPTH; ++l) {
+      warp_gemm_fwd<W / 16, W / 8>(c, ah, sh + L::wdh + (size_t)(l - 1) * W * L::ldh, L::ldh);
+      acc_to_a<W / 8, true>(ah, c);
+    }
+    float co[2][2][4];
+    warp_gemm_fwd<W / 16, 2>(co, ah, sh + L::wdo, L::ldh);
+    store_col0(co, sf + L::fz0, row0);
+    __syncwarp();
+    float rho = valid ? softplus_f(sf[L::fz0 + tid]) * invS : 0.f;
+    // warp-aggregate when the whole warp renders one point
+    const int64_t p0 = __shfl_sync(0xffffffffu, p, 0), p31 = __shfl_sync(0xffffffffu, p, 31);
+    const bool all_valid = __all_sync(0xffffffffu, valid);
+    if (all_valid && p0 == p31) {
+      rho = warp_sum(rho);
+      if (lane == 0) red_add(a.out + p, rho);
+    } else if (valid) {
+      red_add(a.out + p, rho);
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------- host side
+struct MlpLayout {
+  int64_t off_density, off_sigma, off_bias, total;
+};
+
+MlpLayout mlp_layout(const nsv_inr_config& c) {
+  MlpLayout l;
+  const int64_t W = c.width;
+  const int64_t per_density = W * kIn + (int64_t)(c.depth - 1) * W * W + kOutP * W;
+  const int64_t per_head = W * kIn + (int64_t)(c.depth - 1) * W * W + kOutP * W;
+  l.off_density = 0;
+  l.off_sigma = per_density;
+  l.off_bias = l.off_sigma + (c.pixel_variance ? per_head : 0);
+  l.total = l.off_bias + (c.n_levels_bias ? per_head : 0);
+  return l;
+}
+
+int validate_common(const char* name, const nsv_inr_config* c) {
+  NSV_REQUIRE(c != nullptr, "%s: NULL config", name);
+  if (c->grid.n_features != 2 || c->grid.n_levels < 1 || c->grid.n_levels * 2 > kIn) {
+    set_error("%s: fused path needs F=2 and n_levels <= 16 (got F=%d, L=%d)", name, c->grid.n_features, c->grid.n_levels);
+    return NSV_EUNSUPPORTED;
+  }
+  if (!(c->width == 64 || c->width == 32) || c->depth < 1 || c->depth > 3) {
+    set_error("%s: fused path instantiated for width 32|64, depth 1..3 (got %d, %d)", name, c->width, c->depth);
+    return NSV_EUNSUPPORTED;
+  }
+  return NSV_OK;
+}
+
+template <typename K>
+int set_dyn_smem(K kernel, size_t bytes, const char* name) {
+  if (bytes > 227 * 1024) {
+    set_error("%s: configuration needs %zu bytes of shared memory (> 227 KB)", name, bytes);
+    return NSV_EUNSUPPORTED;
+  }
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return NSV_OK;
+}
+
+template <int W, int DEPTH, bool SIGMA>
+int launch_train(const FusedArgs& a, cudaStream_t st) {
+  using L = Layout<W, DEPTH, SIGMA>;
+  if (int e = set_dyn_smem(inr_train_kernel<W, DEPTH, SIGMA>, L::bytes, "nsv_inr_train_step")) return e;
+  const int64_t tiles = a.B * (int64_t)a.S / kTile;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  inr_train_kernel<W, DEPTH, SIGMA><<<grid, kTile, L::bytes, st>>>(a);
+  if (int e = check_launch("nsv_inr_train_step")) return e;
+  inr_finalize_kernel<<<1, 256, 0, st>>>(a.logit_coef, a.g_c, a.losses, a.n_slices, a.cfg.slice_scale, a.cfg.image_reg, a.cfg.delta);
+  return check_launch("nsv_inr_train_step(finalize)");
+}
+
+template <int W, int DEPTH>
+int launch_render(const RenderArgs& a, cudaStream_t st) {
+  using L = Layout<W, DEPTH, false>;
+  if (int e = set_dyn_smem(inr_render_kernel<W, DEPTH>, L::bytes, "nsv_inr_render")) return e;
+  const int64_t tiles = (a.M * (int64_t)a.S + kTile - 1) / kTile;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  inr_render_kernel<W, DEPTH><<<grid, kTile, L::bytes, st>>>(a);
+  return check_launch("nsv_inr_render");
+}
+
+}  // namespace
+}  // namespace nsv
+
+extern "C" int64_t nsv_inr_mlp_layout(const nsv_inr_config* cfg, int64_t* offsets) {
+  if (!cfg) {
+    nsv::set_error("nsv_inr_mlp_layout: NULL config");
+    return NSV_EINVAL;
+  }
+  const nsv::MlpLayout l = nsv::mlp_layout(*cfg);
+  if (offsets) {
+    offsets[0] = l.off_density;
+    offsets[1] = l.off_sigma;
+    offsets[2] = l.off_bias;
+  }
+  return l.total;
+}
+
+extern "C" int nsv_inr_train_step(const nsv_inr_config* cfg, const nsv_inr_params* prm, const nsv_inr_grads* g, const float* xyz,
+                                  const float* v, const int64_t* slice_idx, const float* noise, uint64_t seed, uint64_t offset,
+                                  float* v_out, int64_t B, int S, void* stream) {
+  using namespace nsv;
+  if (int e = validate_common("nsv_inr_train_step", cfg)) return e;
+  NSV_REQUIRE(prm && g && xyz && v && slice_idx, "nsv_inr_train_step: NULL pointer");
+  NSV_REQUIRE(prm->table_f16 && prm->mlp_f16 && prm->axisangle && prm->psf_sigma && g->table && g->mlp && g->losses,
+              "nsv_inr_train_step: NULL parameter / gradient buffer");
+  NSV_REQUIRE(B > 0, "nsv_inr_train_step: B must be positive");
+  int log2S = 0;
+  while ((1 << log2S) < S) ++log2S;
+  if (!(S >= 32 && S <= kTile && (1 << log2S) == S) || (B * (int64_t)S) % kTile != 0) {
+    set_error("nsv_inr_train_step: fused path needs n_samples in {32,64,128,256} and B*S %% 256 == 0 (got B=%lld S=%d)", (long long)B, S);
+    return NSV_EUNSUPPORTED;
+  }
+  if (cfg->n_levels_bias != 0) {
+    set_error("nsv_inr_train_step: the bias-field head (n_levels_bias > 0) is not fused yet");
+    return NSV_EUNSUPPORTED;
+  }
+  if (cfg->pixel_variance && (cfg->depth != 1 || cfg->n_features_slice != 16 || cfg->n_features_z != 15)) {
+    set_error("nsv_inr_train_step: fused sigma_net needs depth 1, n_features_slice 16, n_features_z 15");
+    return NSV_EUNSUPPORTED;
+  }
+  NSV_REQUIRE(!cfg->pixel_variance || prm->slice_embedding, "nsv_inr_train_step: pixel variance needs slice_embedding");
+  NSV_REQUIRE(!cfg->pixel_variance || g->slice_embedding, "nsv_inr_train_step: pixel variance needs grads.slice_embedding");
+  NSV_REQUIRE(!cfg->slice_scale || (prm->logit_coef && g->slice_scale_c), "nsv_inr_train_step: slice scale needs logit_coef and its gradient");
+  NSV_REQUIRE(!cfg->slice_variance || (prm->log_var_slice && g->log_var_slice), "nsv_inr_train_step: slice variance needs log_var_slice and its gradient");
+  NSV_REQUIRE(!cfg->pose_grad || g->axisangle, "nsv_inr_train_step: pose_grad needs grads.axisangle");
+  NSV_REQUIRE(cfg->grad_scale > 0.f, "nsv_inr_train_step: grad_scale must be positive");
+  const MlpLayout ml = mlp_layout(*cfg);
+  FusedArgs a;
+  a.cfg = *cfg;
+  a.table = (const __half*)prm->table_f16;
+  a.mlp = (const __half*)prm->mlp_f16;
+  a.axisangle = prm->axisangle;
+  a.psf_sigma = prm->psf_sigma;
+  a.slice_embedding = prm->slice_embedding;
+  a.logit_coef = prm->logit_coef;
+  a.log_var_slice = prm->log_var_slice;
+  a.n_slices = prm->n_slices;
+  a.g_table = g->table;
+  a.g_mlp = g->mlp;
+  a.g_axisangle = g->axisangle;
+  a.g_se = g->slice_embedding;
+  a.g_c = g->slice_scale_c;
+  a.g_lvs = g->log_var_slice;
+  a.losses = g->losses;
+  a.xyz = xyz;
+  a.v = v;
+  a.slice_idx = slice_idx;
+  a.noise = noise;
+  a.seed = seed;
+  a.offset = offset;
+  a.v_out = v_out;
+  a.B = B;
+  a.S = S;
+  a.log2S = log2S;
+  a.off_density = ml.off_density;
+  a.off_sigma = ml.off_sigma;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool sig = cfg->pixel_variance != 0;
+  if (cfg->width == 64) {
+    if (sig) return launch_train<64, 1, true>(a, st);
+    if (cfg->depth == 1) return launch_train<64, 1, false>(a, st);
+    if (cfg->depth == 2) return launch_train<64, 2, false>(a, st);
+    return launch_train<64, 3, false>(a, st);
+  }
+  if (sig) return launch_train<32, 1, true>(a, st);
+  if (cfg->depth == 1) return launch_train<32, 1, false>(a, st);
+  if (cfg->depth == 2) return launch_train<32, 2, false>(a, st);
+  return launch_train<32, 3, false>(a, st);
+}
+
+extern "C" int nsv_inr_render(const nsv_inr_config* cfg, const nsv_inr_params* prm, const float* xyz, const float* mat,
+                              int mat_per_point, const float* psf_sigma, int sigma_per_point, const float* noise, uint64_t seed,
+                              uint64_t offset, float* out, int64_t M, int S, void* stream) {
+  using namespace nsv;
+  if (int e = validate_common("nsv_inr_render", cfg)) return e;
+  NSV_REQUIRE(prm && prm->table_f16 && prm->mlp_f16, "nsv_inr_render: NULL parameters");
+  NSV_REQUIRE(M >= 0 && S >= 1, "nsv_inr_render: bad sizes");
+  if (M == 0) return NSV_OK;
+  NSV_REQUIRE(xyz && out && (psf_sigma || (S == 1 && !noise)), "nsv_inr_render: NULL pointer");
+  static const float zero_sigma[3] = {0.f, 0.f, 0.f};
+  (void)zero_sigma;
+  RenderArgs a;
+  a.cfg = *cfg;
+  a.table = (const __half*)prm->table_f16;
+  a.mlp = (const __half*)prm->mlp_f16;
+  a.off_density = mlp_layout(*cfg).off_density;
+  a.xyz = xyz;
+  a.mat = mat;
+  a.mat_per_point = mat_per_point;
+  a.psf_sigma = psf_sigma ? psf_sigma : xyz;  // never dereferenced meaningfully when S == 1 without noise (eps = 0)
+  a.sigma_per_point = psf_sigma ? sigma_per_point : 0;
+  a.noise = noise;
+  a.seed = seed;
+  a.offset = offset;
+  a.out = out;
+  a.M = M;
+  a.S = S;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)M * sizeof(float), st);
+  if (e != cudaSuccess) {
+    set_error("nsv_inr_render: cudaMemsetAsync: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  if (cfg->width == 64) {
+    if (cfg->depth == 1) return launch_render<64, 1>(a, st);
+    if (cfg->depth == 2) return launch_render<64, 2>(a, st);
+    return launch_render<64, 3>(a, st);
+  }
+  if (cfg->depth == 1) return launch_render<32, 1>(a, st);
+  if (cfg->depth == 2) return launch_render<32, 2>(a, st);
+  return launch_render<32, 3>(a, st);
+}

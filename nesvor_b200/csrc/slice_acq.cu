@@ -588,8 +588,8 @@ template <typename T>
 int run_forward(const T* transforms, const T* vol, const uint8_t* vol_mask, const uint8_t* slices_mask, const T* psf,
                 T* slices, T* slices_weight, Dims d, T res_slice, int interp_psf, void* stream) {
   if (int e = check_dims("nsv_slice_acq_forward", d)) return e;
-  NSV_REQUIRE(transforms && vol && psf && slices, "nsv_slice_acq_forward: NULL pointer");
   if (d.n == 0) return NSV_OK;
+  NSV_REQUIRE(transforms && vol && psf && slices, "nsv_slice_acq_forward: NULL pointer");
   const size_t smem = psf_smem_bytes<T>(d);
   if (int e = prep(forward_kernel<T>, smem)) return e;
   forward_kernel<T><<<grid_for(d, 8), kThreads, smem, (cudaStream_t)stream>>>(transforms, vol, vol_mask, slices_mask, psf, slices,
@@ -601,8 +601,8 @@ template <typename T>
 int run_backward(const T* transforms, const T* vol, const uint8_t* vol_mask, const T* psf, const T* grad_slices,
                  const uint8_t* slices_mask, T* grad_vol, T* grad_tf, Dims d, T res_slice, int interp_psf, void* stream) {
   if (int e = check_dims("nsv_slice_acq_backward", d)) return e;
-  NSV_REQUIRE(transforms && vol && psf && grad_slices, "nsv_slice_acq_backward: NULL pointer");
   if (d.n == 0 || (!grad_vol && !grad_tf)) return NSV_OK;
+  NSV_REQUIRE(transforms && vol && psf && grad_slices, "nsv_slice_acq_backward: NULL pointer");
   const size_t smem = psf_smem_bytes<T>(d);
   if (int e = prep(backward_kernel<T>, smem)) return e;
   backward_kernel<T><<<grid_for(d, 8), kThreads, smem, (cudaStream_t)stream>>>(transforms, vol, vol_mask, psf, grad_slices,
@@ -615,9 +615,9 @@ template <typename T>
 int run_adjoint_forward(const T* transforms, const T* psf, const T* slices, const uint8_t* slices_mask, const uint8_t* vol_mask,
                         T* vol, T* vol_weight, Dims d, T res_slice, int interp_psf, int equalize, void* stream) {
   if (int e = check_dims("nsv_slice_acq_adjoint_forward", d)) return e;
+  if (d.n == 0) return NSV_OK;
   NSV_REQUIRE(transforms && psf && slices && vol, "nsv_slice_acq_adjoint_forward: NULL pointer");
   NSV_REQUIRE(!equalize || vol_weight, "nsv_slice_acq_adjoint_forward: equalize needs vol_weight");
-  if (d.n == 0) return NSV_OK;
   const size_t smem = psf_smem_bytes<T>(d);
   if (int e = prep(adjoint_forward_kernel<T>, smem)) return e;
   adjoint_forward_kernel<T><<<grid_for(d, 8), kThreads, smem, (cudaStream_t)stream>>>(
@@ -632,7 +632,7 @@ int run_adjoint_backward(const T* transforms, T* grad_vol, const T* vol_weight, 
                          const T* slices, const uint8_t* slices_mask, const T* vol, T* grad_slices, T* grad_tf, Dims d,
                          T res_slice, int interp_psf, int equalize, void* stream) {
   if (int e = check_dims("nsv_slice_acq_adjoint_backward", d)) return e;
-  NSV_REQUIRE(transforms && psf && slices && grad_vol, "nsv_slice_acq_adjoint_backward: NULL pointer");
+  NSV_REQUIRE(grad_vol && (d.n == 0 || (transforms && psf && slices)), "nsv_slice_acq_adjoint_backward: NULL pointer");
   NSV_REQUIRE(!equalize || (vol_weight && vol), "nsv_slice_acq_adjoint_backward: equalize needs vol and vol_weight");
   if (equalize)
     if (int e = run_equalize<T>(grad_vol, vol_weight, 1, (int64_t)d.D * d.H * d.W, stream)) return e;

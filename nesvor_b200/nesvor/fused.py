@@ -1,0 +1,334 @@
+"""Host side of the fused path: packs a `NeSVoR` model into the flat buffers kernel A reads, runs
+`nsv_inr_train_step` + `nsv_adamw_step` per iteration, and renders with `nsv_inr_render`.
+
+What it replaces in the reference: the body of the hot loop (nesvor/nesvor/train.py:179-198:
+autocast forward, GradScaler-scaled backward, AdamW step, zero_grad) and the inference batches of
+nesvor/nesvor/sample.py:23-32,44-50.  The learnable tensors live in ONE flat fp32 buffer
+
+    [ hash table | packed MLP weights | slice_embedding | logit_coef | log_var_slice | axisangle ]
+
+(trainable prefix first) with a parallel gradient buffer, Adam moments and an fp16 shadow of the
+table + weights, so that an iteration is: 1 fused forward/backward launch (+ a 1-block finalize),
+1 AdamW launch over the whole trainable prefix, and -- only when poses are optimised -- the
+batch-independent `transReg` term (models.py:357-363) through the native pose converters.
+"""
+import ctypes
+import math
+from argparse import Namespace
+from typing import Dict, Optional
+
+import torch
+
+from .. import _lib
+from ..transform import RigidTransform
+from .encoding import FusedMLP, HashGridEncoding
+from .models import B_REG, D_LOSS, DS_LOSS, I_REG, INR, S_LOSS, T_REG, NeSVoR
+
+_IMAGE_REG = {"TV": 1, "edge": 2, "L2": 3}
+_SIGMA_Z_SLOT = 16  # packed sigma_net input = [slice embedding (16) | z0..z15]; z0's column is dead
+
+
+class FusedUnsupported(RuntimeError):
+    """The configuration is outside what kernel A is instantiated for (use the unfused native path)."""
+
+
+def _require(cond: bool, why: str) -> None:
+    if not cond:
+        raise FusedUnsupported("fused INR path unsupported: " + why)
+
+
+def make_config(inr: INR, args: Namespace, *, delta: float = 0.0, n_batch_samples: int = 1 << 20,
+                pixel_variance=False, slice_variance=False, slice_scale=False, pose_grad=False) -> _lib.InrConfig:
+    enc = inr.encoding
+    _require(isinstance(enc, HashGridEncoding) and isinstance(inr.density_net, FusedMLP),
+             "model must be built with dtype=float16 (tcnn-style modules); the fp32 nn.Linear branch has biases")
+    _require(enc.n_features_per_level == 2 and enc.n_levels <= 16, "needs n_features_per_level=2 and n_levels<=16")
+    _require(args.width in (32, 64) and 1 <= args.depth <= 3, "needs width in {32,64} and depth in 1..3")
+    _require(inr.density_net.n_out_padded == 16, "needs 1 + n_features_z <= 16")
+    cfg = _lib.InrConfig()
+    cfg.grid = enc.meta
+    cfg.width, cfg.depth = args.width, args.depth
+    cfg.n_features_z, cfg.n_features_slice = args.n_features_z, args.n_features_slice
+    cfg.n_levels_bias = args.n_levels_bias
+    cfg.pixel_variance, cfg.slice_variance = int(pixel_variance), int(slice_variance)
+    cfg.slice_scale, cfg.pose_grad = int(slice_scale), int(pose_grad)
+    cfg.image_reg = _IMAGE_REG[args.image_regularization] if getattr(args, "weight_image", 0) else 0
+    cfg.delta = float(delta)
+    cfg.w_image = float(getattr(args, "weight_image", 0.0))
+    cfg.w_bias = float(getattr(args, "weight_bias", 0.0))
+    bb = inr.bounding_box.detach().float().cpu()
+    for i in range(3):
+        cfg.bbox_lo[i] = float(bb[0, i])
+        cfg.bbox_hi[i] = float(bb[1, i])
+    # loss scale for the fp16 backward operands: dL/dz ~ 1/(B*S); power of two, so unscaling is exact
+    cfg.grad_scale = float(2.0 ** (math.floor(math.log2(max(n_batch_samples, 1))) + 4))
+    return cfg
+
+
+def _mlp_layout(cfg: _lib.InrConfig):
+    off = (ctypes.c_int64 * 3)()
+    total = _lib.lib().nsv_inr_mlp_layout(ctypes.byref(cfg), off)
+    if total < 0:
+        _lib.check(int(total), "nsv_inr_mlp_layout")
+    return int(total), [int(o) for o in off]
+
+
+def _pack_sigma(logical: torch.Tensor, width: int) -> torch.Tensor:
+    """FusedMLP flat params of sigma_net -> packed layout (first layer columns re-slotted)."""
+    w0 = logical[: width * 32].view(width, 32)
+    p0 = torch.zeros_like(w0)
+    p0[:, :16] = w0[:, :16]
+    p0[:, _SIGMA_Z_SLOT + 1 : 32] = w0[:, 16:31]
+    return torch.cat([p0.reshape(-1), logical[width * 32 :]])
+
+
+def _unpack_sigma(packed: torch.Tensor, width: int) -> torch.Tensor:
+    p0 = packed[: width * 32].view(width, 32)
+    w0 = torch.zeros_like(p0)
+    w0[:, :16] = p0[:, :16]
+    w0[:, 16:31] = p0[:, _SIGMA_Z_SLOT + 1 : 32]
+    return torch.cat([w0.reshape(-1), packed[width * 32 :]])
+
+
+class FusedState:
+    """Flat parameter / gradient buffers of one NeSVoR model (or of a bare INR for rendering)."""
+
+    def __init__(self, inr: INR, args: Namespace, model: Optional[NeSVoR] = None, n_batch_samples: int = 1 << 20):
+        self.inr, self.model, self.args = inr, model, args
+        dev = inr.encoding.params.device
+        self.device = dev
+        a = args
+        pv = model is not None and not a.no_pixel_variance
+        sv = model is not None and not a.no_slice_variance
+        sc = model is not None and not a.no_slice_scale
+        pg = model is not None and not a.no_transformation_optimization
+        if model is not None:
+            _require(a.n_levels_bias == 0, "the bias-field head (n_levels_bias > 0) is not fused yet")
+            _require(not pv or (a.depth == 1 and a.n_features_slice == 16 and a.n_features_z == 15),
+                     "fused sigma_net needs depth=1, n_features_slice=16, n_features_z=15")
+        self.cfg = make_config(inr, a, delta=(model.delta if model is not None else 0.0), n_batch_samples=n_batch_samples,
+                               pixel_variance=pv, slice_variance=sv, slice_scale=sc, pose_grad=pg)
+        n_mlp, (self.off_density, self.off_sigma, self.off_bias) = _mlp_layout(self.cfg)
+        n_table = inr.encoding.params.numel()
+        ns = model.n_slices if model is not None else 0
+        # ---- segments: (name, numel, trainable) in buffer order, trainable prefix first ----
+        segs = [("table", n_table, True), ("mlp", n_mlp, True)]
+        if model is not None:
+            tail = []
+            for name, n, used in (("slice_embedding", ns * a.n_features_slice if a.n_features_slice else 0, pv),
+                                  ("logit_coef", ns if sc else 0, sc), ("log_var_slice", ns if sv else 0, sv),
+                                  ("axisangle", ns * 6, pg)):
+                if n == 0:
+                    continue
+                (segs if used else tail).append((name, n, used))
+            segs += tail
+        self.offsets: Dict[str, slice] = {}
+        off = 0
+        self.n_train = 0
+        for name, n, train in segs:
+            n_pad = (n + 3) // 4 * 4  # keep every segment 16-byte aligned
+            self.offsets[name] = slice(off, off + n)
+            off += n_pad
+            if train:
+                self.n_train = off
+        self.n_total = off
+        self.flat = torch.zeros(self.n_total, dtype=torch.float32, device=dev)
+        self.flat16 = torch.zeros(self.n_total, dtype=torch.float16, device=dev)
+        self.grad = torch.zeros(self.n_total + 8, dtype=torch.float32, device=dev)  # + losses[8]
+        self.losses = self.grad[self.n_total : self.n_total + 8]
+        self.psf_sigma = model.psf_sigma.contiguous().float() if model is not None else None
+        self.pull_from_model()
+
+    # ------------------------------------------------------------------ model <-> flat
+    def seg(self, name: str, buf: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+        if name not in self.offsets:
+            return None
+        return (self.flat if buf is None else buf)[self.offsets[name]]
+
+    def pull_from_model(self) -> None:
+        with torch.no_grad():
+            self.seg("table").copy_(self.inr.encoding.params)
+            mlp = self.seg("mlp")
+            d = self.inr.density_net.params
+            mlp[self.off_density : self.off_density + d.numel()].copy_(d)
+            m = self.model
+            if m is not None:
+                if self.cfg.pixel_variance:
+                    s = _pack_sigma(m.sigma_net.params.detach(), self.args.width)
+                    mlp[self.off_sigma : self.off_sigma + s.numel()].copy_(s)
+                for name, t in (("slice_embedding", getattr(getattr(m, "slice_embedding", None), "weight", None)),
+                                ("logit_coef", getattr(m, "logit_coef", None)), ("log_var_slice", getattr(m, "log_var_slice", None)),
+                                ("axisangle", m.axisangle)):
+                    if name in self.offsets and t is not None:
+                        self.seg(name).copy_(t.reshape(-1))
+            self.flat16.copy_(self.flat)
+
+    def push_to_model(self) -> None:
+        with torch.no_grad():
+            self.inr.encoding.params.copy_(self.seg("table"))
+            mlp = self.seg("mlp")
+            d = self.inr.density_net.params
+            d.copy_(mlp[self.off_density : self.off_density + d.numel()])
+            m = self.model
+            if m is not None:
+                if self.cfg.pixel_variance:
+                    n = m.sigma_net.params.numel()
+                    m.sigma_net.params.copy_(_unpack_sigma(mlp[self.off_sigma : self.off_sigma + n], self.args.width))
+                for name, t in (("slice_embedding", getattr(getattr(m, "slice_embedding", None), "weight", None)),
+                                ("logit_coef", getattr(m, "logit_coef", None)), ("log_var_slice", getattr(m, "log_var_slice", None)),
+                                ("axisangle", m.axisangle)):
+                    if name in self.offsets and t is not None:
+                        t.copy_(self.seg(name).view_as(t))
+
+    # ------------------------------------------------------------------ native structs
+    def params_struct(self) -> _lib.InrParams:
+        p = _lib.InrParams()
+        p.table_f16 = self.seg("table", self.flat16).data_ptr()
+        p.mlp_f16 = self.seg("mlp", self.flat16).data_ptr()
+        for name in ("axisangle", "slice_embedding", "logit_coef", "log_var_slice"):
+            t = self.seg(name)
+            setattr(p, name, t.data_ptr() if t is not None and t.numel() else None)
+        p.psf_sigma = self.psf_sigma.data_ptr() if self.psf_sigma is not None else None
+        p.n_slices = self.model.n_slices if self.model is not None else 0
+        return p
+
+    def grads_struct(self) -> _lib.InrGrads:
+        g = _lib.InrGrads()
+        g.table = self.seg("table", self.grad).data_ptr()
+        g.mlp = self.seg("mlp", self.grad).data_ptr()
+        for field, name in (("axisangle", "axisangle"), ("slice_embedding", "slice_embedding"), ("slice_scale_c", "logit_coef"),
+                            ("log_var_slice", "log_var_slice")):
+            t = self.seg(name, self.grad)
+            setattr(g, field, t.data_ptr() if t is not None and t.numel() else None)
+        g.losses = self.losses.data_ptr()
+        return g
+
+    # ------------------------------------------------------------------ one forward+backward
+    def forward_backward(self, xyz, v, slice_idx, noise=None, seed: int = 0, offset: int = 0, want_v_out: bool = False):
+        """Accumulates gradients into `self.grad` (caller zeroes) and returns (losses[8] view, v_out or None)."""
+        B = xyz.shape[0]
+        S = self.args.n_samples
+        xyz = xyz.contiguous().float()
+        v = v.contiguous().float()
+        slice_idx = slice_idx.contiguous().to(torch.int64)
+        if noise is not None:
+            noise = noise.contiguous().float()
+            assert noise.shape == (B, S, 3)
+        v_out = torch.empty(B, dtype=torch.float32, device=xyz.device) if want_v_out else None
+        prm, grd = self.params_struct(), self.grads_struct()
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().nsv_inr_train_step(
+                ctypes.byref(self.cfg), ctypes.byref(prm), ctypes.byref(grd), _lib.ptr(xyz), _lib.ptr(v), _lib.ptr(slice_idx),
+                _lib.ptr(noise), ctypes.c_uint64(seed), ctypes.c_uint64(offset), _lib.ptr(v_out), ctypes.c_int64(B), ctypes.c_int(S),
+                _lib.stream(self.device))
+        if rc == -2:
+            raise FusedUnsupported(_lib.lib().nsv_last_error_string().decode())
+        _lib.check(rc, "nsv_inr_train_step")
+        if self.cfg.pixel_variance:  # the z0 slot of sigma_net's first layer is structurally zero
+            w = self.args.width
+            g0 = self.seg("mlp", self.grad)[self.off_sigma : self.off_sigma + w * 32].view(w, 32)
+            g0[:, _SIGMA_Z_SLOT] = 0
+        return self.losses, v_out
+
+    def loss_dict(self, losses: torch.Tensor) -> Dict[str, torch.Tensor]:
+        a = self.args
+        out = {D_LOSS: losses[0]}
+        if not (a.no_pixel_variance and a.no_slice_variance):
+            out[S_LOSS] = losses[1]
+            out[DS_LOSS] = losses[0] + losses[1]
+        out[I_REG] = losses[3]
+        return out
+
+
+class FusedTrainer:
+    """Drop-in for the body of train()'s loop: `losses = trainer.step(xyz=..., v=..., slice_idx=...)`."""
+
+    def __init__(self, model: NeSVoR, args: Namespace):
+        self.model, self.args = model, args
+        self.state = FusedState(model.inr, args, model, n_batch_samples=args.batch_size * args.n_samples)
+        st = self.state
+        self.exp_avg = torch.zeros(st.n_train, dtype=torch.float32, device=st.device)
+        self.exp_avg_sq = torch.zeros(st.n_train, dtype=torch.float32, device=st.device)
+        self.lr = float(args.learning_rate)
+        self.iteration = 0
+        self.seed = int(getattr(args, "seed", 0) or 0)
+        self.pose = not args.no_transformation_optimization
+
+    def decay_lr(self, gamma: float) -> None:
+        self.lr *= gamma
+
+    def _trans_reg(self) -> torch.Tensor:
+        """transReg (models.py:357-363) on the flat axisangle; its gradient is added to the flat grad."""
+        st = self.state
+        ax = st.seg("axisangle").view(-1, 6).detach().clone().requires_grad_(True)
+        x = RigidTransform(ax, trans_first=True)
+        y = RigidTransform(self.model.axisangle_init, trans_first=True)
+        err = y.inv().compose(x).axisangle(trans_first=True)
+        loss = torch.mean(err[:, :3] ** 2) + 1e-3 * torch.mean(err[:, 3:] ** 2)
+        (g,) = torch.autograd.grad(loss, ax)
+        st.seg("axisangle", st.grad).add_(g.reshape(-1), alpha=float(self.args.weight_transformation))
+        return loss.detach()
+
+    def step(self, xyz, v, slice_idx, noise=None) -> Dict[str, torch.Tensor]:
+        st, a = self.state, self.args
+        self.iteration += 1
+        st.losses.zero_()  # parameter gradients were cleared by the previous AdamW pass
+        n_q = xyz.shape[0] * a.n_samples
+        losses, _ = st.forward_backward(xyz, v, slice_idx, noise, seed=self.seed, offset=(self.iteration - 1) * n_q)
+        out = st.loss_dict(losses.clone())
+        if self.pose and a.weight_transformation:
+            out[T_REG] = self._trans_reg()
+        with torch.cuda.device(st.device):
+            rc = _lib.lib().nsv_adamw_step(
+                _lib.ptr(st.flat), _lib.ptr(st.grad), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), _lib.ptr(st.flat16),
+                ctypes.c_int64(st.n_train), ctypes.c_float(self.lr), ctypes.c_float(0.9), ctypes.c_float(0.99), ctypes.c_float(1e-15),
+                ctypes.c_float(1e-2), ctypes.c_int(self.iteration), ctypes.c_float(1.0), ctypes.c_int(1), _lib.stream(st.device))
+        _lib.check(rc, "nsv_adamw_step")
+        return out
+
+    def sync_to_model(self) -> None:
+        self.state.push_to_model()
+
+
+def fused_render(inr: INR, xyz: torch.Tensor, transformation: Optional[RigidTransform], psf_sigma, n_samples: int,
+                 noise: Optional[torch.Tensor] = None, seed: int = 0, state: Optional[FusedState] = None) -> torch.Tensor:
+    """INR.sample_batch + INR.forward(...).mean(-1) (sample.py:25-31,44-50) in one launch."""
+    if state is None:
+        state = getattr(inr, "_fused_state", None)
+        if state is None:
+            raise RuntimeError("fused_render: attach a FusedState first (attach_render_state(inr, args))")
+    M = xyz.shape[0]
+    S = max(int(n_samples), 1)
+    xyz = xyz.contiguous().float()
+    mat = None
+    per_point = 0
+    if transformation is not None:
+        mat = transformation.matrix(True).contiguous().float()
+        per_point = int(mat.shape[0] > 1)
+        assert mat.shape[0] in (1, M)
+    if isinstance(psf_sigma, torch.Tensor):
+        sig = psf_sigma.to(xyz.device).float().reshape(-1, 3).contiguous() if psf_sigma.numel() > 1 else psf_sigma.to(xyz.device).float().reshape(1).expand(3).contiguous()
+    elif isinstance(psf_sigma, (tuple, list)):
+        sig = torch.tensor([list(psf_sigma)], dtype=torch.float32, device=xyz.device)
+    else:
+        sig = torch.full((1, 3), float(psf_sigma), dtype=torch.float32, device=xyz.device)
+    sig_pp = int(sig.numel() > 3)
+    out = torch.empty(M, dtype=torch.float32, device=xyz.device)
+    prm = state.params_struct()
+    if noise is not None:
+        noise = noise.contiguous().float()
+    with torch.cuda.device(xyz.device):
+        rc = _lib.lib().nsv_inr_render(
+            ctypes.byref(state.cfg), ctypes.byref(prm), _lib.ptr(xyz), _lib.ptr(mat), ctypes.c_int(per_point), _lib.ptr(sig),
+            ctypes.c_int(sig_pp), _lib.ptr(noise), ctypes.c_uint64(seed), ctypes.c_uint64(0), _lib.ptr(out), ctypes.c_int64(M),
+            ctypes.c_int(S), _lib.stream(xyz.device))
+    if rc == -2:
+        raise FusedUnsupported(_lib.lib().nsv_last_error_string().decode())
+    _lib.check(rc, "nsv_inr_render")
+    return out
+
+
+def attach_render_state(inr: INR, args: Namespace) -> FusedState:
+    state = FusedState(inr, args, None)
+    inr._fused_state = state
+    return state

@@ -17,8 +17,10 @@ from .models import INR
 
 def _render(model: INR, xyz, transformation, psf_sigma, n_samples: int, args: Namespace) -> torch.Tensor:
     if getattr(args, "fused", False):
-        from .fused import fused_render
+        from .fused import attach_render_state, fused_render
 
+        if getattr(model, "_fused_state", None) is None:
+            attach_render_state(model, args)  # snapshot of the (trained) parameters in kernel layout
         return fused_render(model, xyz, transformation, psf_sigma, n_samples)
     xyz_batch = model.sample_batch(xyz, transformation, psf_sigma, n_samples)
     return model(xyz_batch, False).mean(-1)

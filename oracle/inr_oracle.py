@@ -57,14 +57,14 @@ class GridMeta:
 
 
 def grid_meta(n_levels: int, n_features: int, log2_hashmap_size: int, base_resolution: int, per_level_scale: float) -> GridMeta:
-    """Level geometry as tcnn lays it out: scale_l = base * s^l - 1 (fp32),
+    """Level geometry as tcnn lays it out: scale_l = fp32(base * s^l - 1),
     res_l = ceil(scale_l) + 1, T_l = min(round_up(res_l^3, 8), 2^log2_T)."""
     scale = np.zeros(n_levels, np.float32)
     res = np.zeros(n_levels, np.int64)
     size = np.zeros(n_levels, np.int64)
-    log2s = np.log2(np.float32(per_level_scale)).astype(np.float32)
+    log2s = math.log2(float(np.float32(per_level_scale)))  # double precision, narrowed once (platform independent)
     for l in range(n_levels):
-        scale[l] = np.exp2(np.float32(l) * log2s).astype(np.float32) * np.float32(base_resolution) - np.float32(1.0)
+        scale[l] = np.float32(2.0 ** (l * log2s) * base_resolution - 1.0)
         res[l] = int(np.ceil(scale[l])) + 1
         dense = min(int(res[l]) ** 3, (2**32 - 1) // 2)
         dense = (dense + 7) // 8 * 8

@@ -19,7 +19,9 @@ SCATTER_TOL = dict(atol=2e-5, rtol=2e-4)
 
 
 def _native_all(c, interp):
-    import nesvor_b200.slice_acquisition.slice_acq as sa
+    import importlib
+
+    sa = importlib.import_module("nesvor_b200.slice_acquisition.slice_acq")  # the package attribute is shadowed by the function
 
     tf, vol, psf = cuda(c["transforms"]), cuda(c["vol"]), cuda(c["psf"])
     vm, sm = cuda(c["vol_mask"]), cuda(c["slices_mask"])
