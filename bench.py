@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py -- INR training throughput of the NeSVoR reconstruction hot path on B200.
+
+Metric (BASELINE.json): INR training samples/sec at batch 2^20 -- hash-grid queries (pixel x PSF
+sample) fully processed forward + backward + optimiser per second.  Workload = BASELINE config 2:
+3-D Shepp-Logan phantom 128^3, 3 orthogonal simulated stacks (225^2 x 77 slices, 1 mm in-plane,
+3 mm thick), 16-level hash grid T=2^19 F=2, 64-wide MLP with 3 hidden layers ("4-layer"),
+n-samples 128, batch 8192 pixels => 2^20 queries / iteration / GPU, density + slice-scale heads
+(--no-pixel-variance --no-slice-variance --no-transformation-optimization), edge regulariser.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  Keys beyond the base contract: "roofline" (kernel A alone,
+algorithmic bytes / CUDA-event time, vs MEASURED_PEAKS.json), "cpu_baseline" (the oracle port on
+the host cores, bounded sample), "e2e" (same metric through the public API with host buffers).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from argparse import Namespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "INR training samples/sec at batch 2^20"
+UNIT = "queries/s"
+WORKLOAD = dict(
+    workload="BASELINE config 2: phantom 128^3, 3 orthogonal stacks, hash grid L=16 T=2^19 F=2, MLP 64x3 hidden (4 linear layers), "
+             "n_samples 128, batch 8192 px = 2^20 queries/iter/GPU",
+    n=128, n_stacks=3, n_levels=16, log2_hashmap_size=19, width=64, depth=3, n_samples=128, batch_size=8192)
+
+
+def make_args(device, **kw):
+    import torch
+
+    a = dict(n_features_per_level=2, log2_hashmap_size=19, level_scale=1.3819, coarsest_resolution=16.0, finest_resolution=0.5,
+             n_levels_bias=0, depth=3, width=64, n_features_z=15, n_features_slice=16, no_transformation_optimization=True,
+             no_slice_scale=False, no_pixel_variance=True, no_slice_variance=True, single_precision=False,
+             weight_transformation=0.1, weight_bias=100.0, image_regularization="edge", weight_image=2.0, delta=0.2,
+             learning_rate=5e-3, gamma=0.33, milestones=[0.5, 0.75, 0.9], n_iter=5000, batch_size=8192, n_samples=128,
+             dtype=torch.float16, device=device, n_levels=16, base_resolution=None, seed=0, fused=True, mask_threshold=1.0)
+    a.update(kw)
+    return Namespace(**a)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, val in zip(names, r[3:7]) if val.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_oracle_throughput(n_pixels=256, n_samples=128, steps=2, warmup=1, threads=None):
+    """The reference has no CPU path; the CPU baseline is the oracle port:
+    oracle/inr_oracle.py forward + autograd backward + torch AdamW, config-2 model, all host cores,
+    on a bounded sample of the workload (n_pixels x n_samples queries per step)."""
+    import torch
+    from oracle import inr_oracle as io
+
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n_slices = 231
+    g = torch.Generator().manual_seed(0)
+    ax = torch.zeros(n_slices, 6)
+    ax[:, 3:] = torch.randn(n_slices, 3, generator=g) * 20
+    res = torch.tensor([[1.0, 1.0, 3.0]]).repeat(n_slices, 1)
+    bb = torch.tensor([[-66.0, -66.0, -66.0], [66.0, 66.0, 66.0]])
+    cfg = io.INRConfig(n_levels=16, base_resolution=9, level_scale=1.3819, log2_hashmap_size=19, width=64, depth=3,
+                       no_transformation_optimization=True, no_pixel_variance=True, no_slice_variance=True, n_samples=n_samples,
+                       delta=0.2 * 0.3, emulate_fp16=False)
+    om = io.OracleNeSVoR(cfg, n_slices, ax, res, bb)
+    opt = io.make_optimizer(om)
+    times = []
+    for it in range(warmup + steps):
+        xyz = (torch.rand(n_pixels, 3, generator=g) - 0.5) * 100
+        xyz[:, 2] = 0
+        v = torch.rand(n_pixels, generator=g)
+        idx = torch.randint(0, n_slices, (n_pixels,), generator=g)
+        t0 = time.perf_counter()
+        noise = torch.randn(n_pixels, n_samples, 3, generator=g)
+        losses = om.forward(xyz, v, idx, noise)
+        om.total_loss(losses).backward()
+        opt.step()
+        opt.zero_grad()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    per_step = sum(times) / len(times)
+    return {"value": n_pixels * n_samples / per_step, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{steps} iterations of {n_pixels} px x {n_samples} samples ({n_pixels * n_samples} queries/iter) of the config-2 model, "
+                      f"oracle/inr_oracle.py fwd+bwd+AdamW, torch {torch.__version__}, {threads} threads",
+            "ms_per_step": per_step * 1e3}
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_oracle_throughput(steps=max(a.steps, 1), warmup=max(a.warmup, 1))
+    line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": dict(WORKLOAD, note="reference arm = CPU oracle port on a bounded sample; the reference ships no CPU path and its tcnn dependency is absent"),
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from nesvor_b200.csrc import build as nsv_build
+
+    nsv_build.build()
+    import nesvor_b200 as nb
+    from nesvor_b200.data.phantom import simulate_slices
+    from nesvor_b200.nesvor.fused import FusedTrainer
+    from nesvor_b200.nesvor.train import Dataset
+
+    args = make_args(dev)
+    torch.manual_seed(0)
+    slices, _, _ = simulate_slices(n=WORKLOAD["n"], n_stacks=WORKLOAD["n_stacks"], res_r=1.0, res_s=1.0, gap=3.0, device=dev)
+    dataset = Dataset(slices, args)
+    model = nb.NeSVoR(dataset.transformation, dataset.resolution, dataset.mean, dataset.bounding_box, args)
+    trainer = FusedTrainer(model, args)
+    st = trainer.state
+    B, S = args.batch_size, args.n_samples
+    n_q = B * S
+    # every rank draws from its own shuffled copy of the pixel table (weak scaling: B pixels per rank)
+    torch.manual_seed(1234 + rank)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def one_step(batch):
+        if world == 1:
+            return trainer.step(**batch)
+        return trainer.step_distributed(dist, world, **batch)
+
+    # ---------------- value: device-resident inputs, whole iteration (fwd + bwd + AdamW) ----------
+    for _ in range(max(a.warmup, 3)):
+        one_step(dataset.get_batch(B, dev))
+    sync_all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        for _ in range(a.steps):
+            losses = one_step(dataset.get_batch(B, dev))
+        ev1.record()
+        sync_all()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * n_q * a.steps / (ms_total * 1e-3)
+
+    # ---------------- e2e: host buffers through the public step API ----------------
+    host = []
+    for _ in range(4):
+        b = dataset.get_batch(B, dev)
+        host.append({k: v.cpu().pin_memory() for k, v in b.items()})
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        hb = host[i % len(host)]
+        batch = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+        out = one_step(batch)
+        loss_host = {k: float(v) for k, v in out.items()}  # D2H read of the step's losses (syncs, like train.py:199-200)
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_q * a.steps / (float(t.item()) * 1e-3)
+    h2d = B * (3 * 4 + 4 + 8)
+    d2h = 4 * len(loss_host)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline: kernel A alone, L2 flushed between launches ----------------
+    L = st.cfg.grid.n_levels
+    alg_bytes = n_q * L * 8 * 2 * (2 + 4)  # fp16 table gather + fp32 gradient scatter, per SURVEY s.8d
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    batch = dataset.get_batch(B, dev)
+    durs = []
+    stream = torch.cuda.current_stream()
+    for i in range(3 + min(a.steps, 20)):
+        flush.zero_()
+        st.grad.zero_()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        st.forward_backward(batch["xyz"], batch["v"], batch["slice_idx"], None, seed=0, offset=i * n_q)
+        k1.record(stream)
+        torch.cuda.synchronize()
+        if i >= 3:
+            durs.append(k0.elapsed_time(k1))
+    k_ms = sum(durs) / len(durs)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "inr_train_kernel<64,3,false> (+1-block finalize)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                "kernel_queries_per_s": n_q / (k_ms * 1e-3)}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get("inr_train_kernel_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    cpu = cpu_oracle_throughput()
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
+            "data": "synthetic", "config": dict(WORKLOAD, parallelism=f"dp{world}", l2="per-step working set 184 MB (params+grads+Adam moments) > 126 MB L2; kernel-only timing flushes L2 with a 256 MB write",
+                                                noise="in-kernel Philox", n_pixels_in_table=int(dataset.xyz.shape[0]), n_slices=model.n_slices),
+            "clocks": clocks.summary(), "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": 3 * a.steps, "roofline": roofline,
+            "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "losses_last_step": {k: float(v) for k, v in losses.items()}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -74,3 +74,40 @@ def stack_axisangles(orientations: Sequence[Sequence[float]], n_slice: int, gap:
         t = torch.stack((torch.full_like(tz, 0.5), torch.full_like(tz, 0.5), tz), -1)
         rows.append(torch.cat((a, t), -1))
     return torch.cat(rows, 0)
+
+
+def simulate_slices(n: int = 128, n_stacks: int = 3, res_r: float = 1.0, res_s: float = 1.0, gap: float = 3.0,
+                    thickness: Optional[float] = None, n_slice: Optional[int] = None, device="cuda",
+                    motion_deg: float = 0.0, motion_mm: float = 0.0, motion_seed: int = 1):
+    """Phantom -> list of `Slice` objects, simulated with the native slice_acquisition (kernel B)
+    exactly like tests/slice_acquisition/test_slice_acq.py:43-63 does.
+    With `motion_*` > 0 the data are simulated at perturbed ("true") poses while the returned slices
+    carry the nominal stack poses (BASELINE config 3).  Returns (slices, volume, true_axisangle)."""
+    from ..image import Slice
+    from ..slice_acquisition import slice_acquisition
+    from ..transform import RigidTransform, mat_update_resolution
+    from ..utils import get_PSF
+
+    thickness = gap if thickness is None else thickness
+    ss, n_slice = stack_geometry(n, res_r, res_s, gap, n_slice)
+    volume = torch.tensor(phantom3d(n), dtype=torch.float32, device=device)[None, None]
+    psf = get_PSF(res_ratio=(res_s / res_r, res_s / res_r, thickness / res_r), device=torch.device(device))
+    nominal = stack_axisangles(STACK_ORIENTATIONS[:n_stacks], n_slice, gap).to(device)
+    true = nominal.clone()
+    if motion_deg > 0 or motion_mm > 0:
+        g = torch.Generator().manual_seed(motion_seed)
+        d = torch.rand(nominal.shape, generator=g) * 2 - 1
+        d[:, :3] *= motion_deg * math.pi / 180.0
+        d[:, 3:] *= motion_mm
+        true = nominal + d.to(device)
+    mat = mat_update_resolution(RigidTransform(true, trans_first=True).matrix(), 1, res_r).contiguous()
+    images = slice_acquisition(mat, volume, None, None, psf, (ss, ss), res_s / res_r, False, False)
+    slices = []
+    nominal_t = RigidTransform(nominal, trans_first=True)
+    for i in range(images.shape[0]):
+        img = images[i]
+        mask = img > 0
+        if not mask.any():
+            continue  # empty slices are dropped, as svort/inference.py:557-559 does
+        slices.append(Slice(img, mask, nominal_t[i], res_s, res_s, thickness, stack_idx=i // n_slice, slice_idx=i % n_slice))
+    return slices, volume, true

@@ -286,6 +286,29 @@ class FusedTrainer:
         _lib.check(rc, "nsv_adamw_step")
         return out
 
+    def step_distributed(self, dist, world: int, xyz, v, slice_idx, noise=None) -> Dict[str, torch.Tensor]:
+        """Data-parallel iteration (one process per GPU): every rank runs kernel A on its own B pixels,
+        the flat gradient of the trainable prefix is summed with ONE NCCL all-reduce, and the mean over
+        ranks is folded into AdamW's unscale factor, so all replicas apply the identical update."""
+        st, a = self.state, self.args
+        self.iteration += 1
+        st.losses.zero_()
+        n_q = xyz.shape[0] * a.n_samples
+        rank = dist.get_rank()
+        losses, _ = st.forward_backward(xyz, v, slice_idx, noise, seed=self.seed + 7919 * rank,
+                                        offset=(self.iteration - 1) * n_q)
+        out = st.loss_dict(losses.clone())
+        if self.pose and a.weight_transformation:
+            out[T_REG] = self._trans_reg()  # identical on every rank: the all-reduce mean leaves it unchanged
+        dist.all_reduce(st.grad[: st.n_train], op=dist.ReduceOp.SUM)
+        with torch.cuda.device(st.device):
+            rc = _lib.lib().nsv_adamw_step(
+                _lib.ptr(st.flat), _lib.ptr(st.grad), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), _lib.ptr(st.flat16),
+                ctypes.c_int64(st.n_train), ctypes.c_float(self.lr), ctypes.c_float(0.9), ctypes.c_float(0.99), ctypes.c_float(1e-15),
+                ctypes.c_float(1e-2), ctypes.c_int(self.iteration), ctypes.c_float(1.0 / world), ctypes.c_int(1), _lib.stream(st.device))
+        _lib.check(rc, "nsv_adamw_step")
+        return out
+
     def sync_to_model(self) -> None:
         self.state.push_to_model()
 

@@ -115,26 +115,40 @@ def _cg(A, b, x0, n_iter, tol):  # nesvor/svort/srr.py:12-34
         rr = rr_new
 
 
-def test_cg_recovers_phantom_known_answer(native_lib):
-    """The reference's only KAT for A / A^T (tests/slice_acquisition/test_slice_acq.py:76-81)."""
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_cg_recovers_phantom_known_answer(native_lib, dtype):
+    """The reference's only KAT for A / A^T (tests/slice_acquisition/test_slice_acq.py:76-81): CG
+    started AT the phantom must stay there, i.e. A^T(A x) evaluated twice must agree to round-off.
+    The scatter A^T uses float atomics, so in fp32 the residual is summation-order noise (~1e-7
+    relative) which CG divides by the smallest eigenvalues of A^T A; whether the reference's
+    atol=3e-5 holds then depends on the atomic order of the run (it does on most).  The KAT is
+    therefore asserted at the reference tolerance in fp64 (same kernels, order noise ~1e-16) and
+    with the noise-amplification bound 2e-3 in fp32."""
     import nesvor_b200 as nb
     from nesvor_b200.data.phantom import phantom3d, stack_axisangles, stack_geometry
 
     vs, gap, res, res_s = 32, 3.0, 1.0, 1.5
     ss, n_slice = stack_geometry(vs, res, res_s, gap)
-    volume = torch.tensor(phantom3d(vs), dtype=torch.float32).cuda()[None, None]
-    psf = nb.get_PSF(res_ratio=(res_s / res, res_s / res, gap / res)).cuda()
+    volume = torch.tensor(phantom3d(vs), dtype=dtype).cuda()[None, None]
+    psf = nb.get_PSF(res_ratio=(res_s / res, res_s / res, gap / res)).cuda().to(dtype)
     pi = np.pi
     angles = [[0, 0, 0], [pi / 2, 0, 0], [0, pi / 2, 0], [0, 0, pi / 2], [pi / 4, pi / 4, 0], [0, pi / 4, pi / 4],
               [pi / 4, 0, pi / 4], [pi / 3, pi / 3, 0], [0, pi / 3, pi / 3], [pi / 3, 0, pi / 3], [2 * pi / 3, 2 * pi / 3, 0],
               [0, 2 * pi / 3, 2 * pi / 3], [2 * pi / 3, 0, 2 * pi / 3], [pi / 5, pi / 5, 0], [0, pi / 5, pi / 5], [pi / 5, 0, pi / 5]]
     transform = nb.RigidTransform(stack_axisangles(angles, n_slice, gap).cuda(), trans_first=True)
-    theta = nb.mat_update_resolution(transform.matrix(), 1, res).contiguous()
+    theta = nb.mat_update_resolution(transform.matrix(), 1, res).to(dtype).contiguous()
     A = lambda x: nb.slice_acquisition(theta, x, None, None, psf, (ss, ss), res_s / res, False, False)
     At = lambda y: nb.slice_acquisition_adjoint(theta, psf, y, None, None, (vs, vs, vs), res_s / res, False, False)
     slices = A(volume)
     rec = torch.relu(_cg(lambda x: At(A(x)), At(slices), volume, 20, 1e-8))
-    torch.testing.assert_close(rec, volume, atol=3e-5, rtol=1e-5)
+    if dtype == torch.float64:
+        torch.testing.assert_close(rec, volume, atol=3e-5, rtol=1e-5)
+    else:
+        torch.testing.assert_close(rec, volume, atol=2e-3, rtol=1e-5)
+    # and a non-trivial start: 20 CG iterations from zero reduce the data residual by > 100x
+    rec0 = _cg(lambda x: At(A(x)), At(slices), torch.zeros_like(volume), 20, 0.0)
+    r0, r1 = float(slices.norm()), float((A(rec0) - slices).norm())
+    assert r1 < 1e-2 * r0, (r0, r1)
 
 
 def test_adjointness_at_baseline_size(native_lib):
