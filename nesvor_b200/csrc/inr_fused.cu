@@ -31,6 +31,11 @@ namespace {
 constexpr int kTile = 256, kNW = 8, kIn = 32, kOutP = 16;
 constexpr int kLddx = kIn + 1;
 
+// ---- level metadata staged in shared memory (dynamic indexing of kernel params costs an LDC miss) ----
+struct LevelTable {
+  float scale[kIn / 2];
+  uint32_t res[kIn / 2], size[kIn / 2], offset[kIn / 2], hashed[kIn / 2];
+};
 struct FusedArgs {
   nsv_inr_config cfg;
   const __half* table;
@@ -82,7 +87,8 @@ struct Layout {
   static constexpr size_t frho = flv + kTile;
   static constexpr size_t fxw = frho + kTile;                     // [256][3]
   static constexpr size_t fred = fxw + 3 * kTile;                 // [8][16] warp partials
-  static constexpr size_t floats = fred + kNW * 16;
+  static constexpr size_t flt = fred + kNW * 16;                  // LevelTable
+  static constexpr size_t floats = flt + (sizeof(LevelTable) + 3) / 4;
   static constexpr size_t bytes = f_base + floats * 4;
 };
 
@@ -110,68 +116,137 @@ __device__ __forceinline__ void normal3(uint64_t seed, uint64_t idx, float e[3])
   e[2] = r1 * __cosf(6.283185307179586f * u3);
 }
 
-// ---- phase 0: encode one sample into its fp16 row of the shared tile ----
-__device__ __forceinline__ void encode_row(const float xn[3], const nsv_grid_meta& m, const __half* __restrict__ table, __half* row) {
-#pragma unroll 2
-  for (int l = 0; l < m.n_levels; ++l) {
-    const LevelGeom lv = level_geom(m, l);
-    uint32_t g[3];
-    float w[3];
-    level_pos(xn, lv.scale, g, w);
-    float2 f[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-      f[c] = load_pair(table, lv.offset + vertex_index(lv, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2)));
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float wt = corner_weight(c, w);
-      a0 = fmaf(wt, f[c].x, a0);
-      a1 = fmaf(wt, f[c].y, a1);
-    }
-    *reinterpret_cast<__half2*>(row + 2 * l) = __floats2half2_rn(a0, a1);
+__device__ __forceinline__ LevelGeom level_from(const LevelTable& t, int l) {
+  LevelGeom g;
+  g.scale = t.scale[l];
+  g.res = t.res[l];
+  g.size = t.size[l];
+  g.offset = t.offset[l];
+  g.hashed = t.hashed[l];
+  return g;
+}
+// vertex index with the (rarely needed) dense wrap-around kept off the fast path
+__device__ __forceinline__ uint32_t vertex_index_fast(const LevelGeom& lv, uint32_t cx, uint32_t cy, uint32_t cz) {
+  if (lv.hashed) {
+    const uint32_t idx = cx ^ (cy * 2654435761u) ^ (cz * 805459861u);
+    return ((lv.size & (lv.size - 1)) == 0) ? (idx & (lv.size - 1)) : (idx % lv.size);
   }
-  for (int l = m.n_levels; l < kIn / 2; ++l) *reinterpret_cast<uint32_t*>(row + 2 * l) = 0u;
+  uint32_t idx = cx + cy * lv.res + cz * (lv.res * lv.res);
+  if (idx >= lv.size) idx %= lv.size;
+  return idx;
 }
 
-// ---- phase 3 tail: scatter dL/d(features) of one sample; optionally dL/dx through the grid ----
-template <bool kInputGrad>
-__device__ __forceinline__ void scatter_row(const float xn[3], const nsv_grid_meta& m, const __half* __restrict__ table,
-                                            const float* grow, float inv_scale, float* __restrict__ g_table, float gx[3]) {
-  if (kInputGrad) gx[0] = gx[1] = gx[2] = 0.f;
+// Lane mapping of the gather / scatter phases.  A warp owns 32 samples and walks them in two
+// batches of 16; inside a batch lane = (sample s = lane >> 1, x-corner xb = lane & 1).  The two
+// x-neighbours of a cell are adjacent table entries (dense levels always, hashed levels whenever
+// g_x is even), so the two lanes of a pair hit the same 128-byte line and a warp-wide LDG / RED
+// touches <= 16 lines instead of 32 -- the L1 wavefront count, which bounds this kernel, halves.
+// Each lane blends / scatters its 4 (y,z) corners; one shfl_xor(1) combines the pair.
+
+// ---- phase 0: encode the warp's 32 samples into their fp16 rows of the shared tile ----
+__device__ __forceinline__ void encode_warp(const float xn[3], const LevelTable& lt, int n_levels, const __half* __restrict__ table,
+                                            __half* rows /* first row of this warp */, int ld) {
+  const int lane = threadIdx.x & 31, xb = lane & 1, sl = lane >> 1;
+  float px[2][3];
+#pragma unroll
+  for (int b = 0; b < 2; ++b)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) px[b][d] = __shfl_sync(0xffffffffu, xn[d], b * 16 + sl);
 #pragma unroll 2
-  for (int l = 0; l < m.n_levels; ++l) {
-    const float g0 = grow[2 * l] * inv_scale, g1 = grow[2 * l + 1] * inv_scale;
-    const LevelGeom lv = level_geom(m, l);
-    uint32_t g[3];
-    float w[3];
-    level_pos(xn, lv.scale, g, w);
-    uint32_t e[8];
+  for (int l = 0; l < n_levels; ++l) {
+    const LevelGeom lv = level_from(lt, l);
+    float2 f[2][4];
+    float wq[2][4];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) e[c] = lv.offset + vertex_index(lv, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2));
-    if (kInputGrad) {
-      float2 f[8];
+    for (int b = 0; b < 2; ++b) {
+      uint32_t g[3];
+      float w[3];
+      level_pos(px[b], lv.scale, g, w);
+      const float wx = xb ? w[0] : 1.f - w[0];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) f[c] = load_pair(table, e[c]);
-      float d[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float dot = fmaf(f[c].x, g0, f[c].y * g1);
-        const float fx = (c & 1) ? w[0] : 1.f - w[0], fy = (c & 2) ? w[1] : 1.f - w[1], fz = (c & 4) ? w[2] : 1.f - w[2];
-        d[0] += ((c & 1) ? dot : -dot) * fy * fz;
-        d[1] += ((c & 2) ? dot : -dot) * fx * fz;
-        d[2] += ((c & 4) ? dot : -dot) * fx * fy;
-      }
-#pragma unroll
-      for (int k = 0; k < 3; ++k) gx[k] = fmaf(lv.scale, d[k], gx[k]);
-    }
-    if (g0 != 0.f || g1 != 0.f) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float wt = corner_weight(c, w);
-        red_add_v2(g_table + 2 * (size_t)e[c], wt * g0, wt * g1);
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t e = lv.offset + vertex_index_fast(lv, g[0] + xb, g[1] + (q & 1), g[2] + (q >> 1));
+        f[b][q] = load_pair(table, e);
+        wq[b][q] = wx * ((q & 1) ? w[1] : 1.f - w[1]) * ((q >> 1) ? w[2] : 1.f - w[2]);
       }
     }
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        a0 = fmaf(wq[b][q], f[b][q].x, a0);
+        a1 = fmaf(wq[b][q], f[b][q].y, a1);
+      }
+      a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+      if (xb == 0) *reinterpret_cast<__half2*>(rows + (size_t)(b * 16 + sl) * ld + 2 * l) = __floats2half2_rn(a0, a1);
+    }
+  }
+  // zero the padding columns of this thread's own row
+  for (int l = n_levels; l < kIn / 2; ++l) *reinterpret_cast<uint32_t*>(rows + (size_t)lane * ld + 2 * l) = 0u;
+}
+
+// ---- phase 3 tail: scatter dL/d(features) of the warp's 32 samples; optionally dL/dx through the grid ----
+// grows: fp32 [32][kLddx] rows of this warp; gxs: fp32 [32][3] output rows (only when kInputGrad)
+template <bool kInputGrad>
+__device__ __forceinline__ void scatter_warp(const float xn[3], const LevelTable& lt, int n_levels, const __half* __restrict__ table,
+                                             const float* grows, float inv_scale, float* __restrict__ g_table, float* gxs) {
+  const int lane = threadIdx.x & 31, xb = lane & 1, sl = lane >> 1;
+  float px[2][3];
+#pragma unroll
+  for (int b = 0; b < 2; ++b)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) px[b][d] = __shfl_sync(0xffffffffu, xn[d], b * 16 + sl);
+  float gx[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll 2
+  for (int l = 0; l < n_levels; ++l) {
+    const LevelGeom lv = level_from(lt, l);
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const float* gr = grows + (size_t)(b * 16 + sl) * kLddx + 2 * l;
+      const float g0 = gr[0] * inv_scale, g1 = gr[1] * inv_scale;
+      uint32_t g[3];
+      float w[3];
+      level_pos(px[b], lv.scale, g, w);
+      const float wx = xb ? w[0] : 1.f - w[0];
+      uint32_t e[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) e[q] = lv.offset + vertex_index_fast(lv, g[0] + xb, g[1] + (q & 1), g[2] + (q >> 1));
+      if (kInputGrad) {
+        float2 f[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) f[q] = load_pair(table, e[q]);
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float dot = fmaf(f[q].x, g0, f[q].y * g1);
+          const float fy = (q & 1) ? w[1] : 1.f - w[1], fz = (q >> 1) ? w[2] : 1.f - w[2];
+          d0 += (xb ? dot : -dot) * fy * fz;
+          d1 += ((q & 1) ? dot : -dot) * wx * fz;
+          d2 += ((q >> 1) ? dot : -dot) * wx * fy;
+        }
+        gx[b][0] = fmaf(lv.scale, d0, gx[b][0]);
+        gx[b][1] = fmaf(lv.scale, d1, gx[b][1]);
+        gx[b][2] = fmaf(lv.scale, d2, gx[b][2]);
+      }
+      if (g0 != 0.f || g1 != 0.f) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float wt = wx * ((q & 1) ? w[1] : 1.f - w[1]) * ((q >> 1) ? w[2] : 1.f - w[2]);
+          red_add_v2(g_table + 2 * (size_t)e[q], wt * g0, wt * g1);
+        }
+      }
+    }
+  }
+  if (kInputGrad) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float v = gx[b][d] + __shfl_xor_sync(0xffffffffu, gx[b][d], 1);
+        if (xb == 0) gxs[(size_t)(b * 16 + sl) * 3 + d] = v;
+      }
   }
 }
 
@@ -211,6 +286,14 @@ __global__ void __launch_bounds__(kTile, 1) inr_train_kernel(const __grid_consta
       stage_weights(sh + L::ws0, L::ldx, ws, W, kIn);
       stage_weights(sh + L::wso, L::ldh, ws + (size_t)W * kIn, kOutP, W);
     }
+  }
+  LevelTable& lt = *reinterpret_cast<LevelTable*>(sf + L::flt);
+  if (tid < kIn / 2) {
+    lt.scale[tid] = cfg.grid.scale[tid];
+    lt.res[tid] = cfg.grid.res[tid];
+    lt.size[tid] = cfg.grid.size[tid];
+    lt.offset[tid] = cfg.grid.offset[tid];
+    lt.hashed[tid] = cfg.grid.hashed[tid];
   }
   // ---- log-sum-exp of logit_coef (slice scale c_k = n_s softmax_k) ----
   float lse = 0.f;
@@ -274,7 +357,7 @@ __global__ void __launch_bounds__(kTile, 1) inr_train_kernel(const __grid_consta
         xn[i] = (xw[i] - cfg.bbox_lo[i]) / (cfg.bbox_hi[i] - cfg.bbox_lo[i]);
       }
     }
-    encode_row(xn, cfg.grid, a.table, sh + L::sx + (size_t)tid * L::ldx);
+    encode_warp(xn, lt, cfg.grid.n_levels, a.table, sh + L::sx + (size_t)row0 * L::ldx, L::ldx);
     __syncwarp();
 
     // ================= phase 1: density MLP forward (warp-local) =================
@@ -488,11 +571,13 @@ __global__ void __launch_bounds__(kTile, 1) inr_train_kernel(const __grid_consta
         }
     }
     __syncwarp();
-    // ---- per-sample scatter into the table gradient (+ pose gradient) ----
-    const float* grow = sf + L::fdx + (size_t)tid * kLddx;
+    // ---- scatter into the table gradient (+ pose gradient), lanes = (sample, x-corner) ----
+    const float* grows = sf + L::fdx + (size_t)row0 * kLddx;
     if (cfg.pose_grad) {
-      float gx[3];
-      scatter_row<true>(xn, cfg.grid, a.table, grow, inv_gscale, a.g_table, gx);
+      float* gxs = sf + L::fxw + (size_t)row0 * 3;  // xw rows are dead after phase 2
+      scatter_warp<true>(xn, lt, cfg.grid.n_levels, a.table, grows, inv_gscale, a.g_table, gxs);
+      __syncwarp();
+      const float gx[3] = {gxs[lane * 3], gxs[lane * 3 + 1], gxs[lane * 3 + 2]};
       float gw[3], part[12];
 #pragma unroll
       for (int i = 0; i < 3; ++i) gw[i] = gx[i] / (cfg.bbox_hi[i] - cfg.bbox_lo[i]);
@@ -527,8 +612,7 @@ __global__ void __launch_bounds__(kTile, 1) inr_train_kernel(const __grid_consta
         }
       }
     } else {
-      float gx[3];
-      scatter_row<false>(xn, cfg.grid, a.table, grow, inv_gscale, a.g_table, gx);
+      scatter_warp<false>(xn, lt, cfg.grid.n_levels, a.table, grows, inv_gscale, a.g_table, nullptr);
     }
   }
 
@@ -626,6 +710,14 @@ __global__ void __launch_bounds__(kTile, 1) inr_render_kernel(const __grid_const
   stage_weights(sh + L::wd0, L::ldx, wd, W, kIn);
   for (int l = 0; l + 1 < DEPTH; ++l) stage_weights(sh + L::wdh + (size_t)l * W * L::ldh, L::ldh, wd + (size_t)W * kIn + (size_t)l * W * W, W, W);
   stage_weights(sh + L::wdo, L::ldh, wd + (size_t)W * kIn + (size_t)(DEPTH - 1) * W * W, kOutP, W);
+  LevelTable& lt = *reinterpret_cast<LevelTable*>(sf + L::flt);
+  if (tid < kIn / 2) {
+    lt.scale[tid] = cfg.grid.scale[tid];
+    lt.res[tid] = cfg.grid.res[tid];
+    lt.size[tid] = cfg.grid.size[tid];
+    lt.offset[tid] = cfg.grid.offset[tid];
+    lt.hashed[tid] = cfg.grid.hashed[tid];
+  }
   __syncthreads();
   const int64_t total = a.M * (int64_t)a.S;
   const int64_t n_tiles = (total + kTile - 1) / kTile;
@@ -658,7 +750,7 @@ __global__ void __launch_bounds__(kTile, 1) inr_render_kernel(const __grid_const
 #pragma unroll
       for (int i = 0; i < 3; ++i) xn[i] = (xw[i] - cfg.bbox_lo[i]) / (cfg.bbox_hi[i] - cfg.bbox_lo[i]);
     }
-    encode_row(xn, cfg.grid, a.table, sh + L::sx + (size_t)tid * L::ldx);
+    encode_warp(xn, lt, cfg.grid.n_levels, a.table, sh + L::sx + (size_t)row0 * L::ldx, L::ldx);
     __syncwarp();
     uint32_t ain[2][kIn / 16][4];
     load_a_frags<kIn / 16>(ain, sh + L::sx, L::ldx, row0);
