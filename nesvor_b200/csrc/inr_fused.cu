@@ -28,7 +28,9 @@
 namespace nsv {
 namespace {
 
-constexpr int kTile = 256, kNW = 8, kIn = 32, kOutP = 16;
+constexpr int kTile = 256;     // sample rows per CTA
+constexpr int kThreads = 512;  // 16 warps; a warp owns 16 rows, lane = (row = lane >> 1, x-corner = lane & 1)
+constexpr int kIn = 32, kOutP = 16;
 constexpr int kLddx = kIn + 1;
 
 // ---- level metadata staged in shared memory (dynamic indexing of kernel params costs an LDC miss) ----
@@ -64,32 +66,62 @@ struct FusedArgs {
   int64_t off_density, off_sigma;
 };
 
-template <int W, int DEPTH, bool SIGMA>
+// Shared-memory plan.  A CTA hosts NG = 256/GR independent groups of GR rows (GR/32 warps); each
+// group owns its activation tiles, the CTA shares weights, level table and the fp32 weight-gradient
+// accumulators.  With GR = 128 the two groups run out of phase (named barriers), so one group's
+// tensor-core phases overlap the other's gather / scatter phases.
+template <int W, int DEPTH, bool SIGMA, int GR>
 struct Layout {
+  static constexpr int NG = kTile / GR, GW = GR / 16;
   static constexpr int ldx = kIn + kPad, ldh = W + kPad, ldg = kOutP + kPad;
-  // fp16 region (offsets in halves)
+  static constexpr bool alias_dx = DEPTH >= 2 && (W + kPad) * 2 >= kLddx * 4;  // dL/d(features) tile reuses the dead H_last slot
+  static_assert((size_t)GR * kLddx * 4 <= (size_t)GR * ldh * 2 || !alias_dx, "dX does not fit the aliased slot");
+  // ---- CTA-shared fp16 weights (offsets in halves) ----
   static constexpr size_t wd0 = 0;
   static constexpr size_t wdh = wd0 + (size_t)W * ldx;
   static constexpr size_t wdo = wdh + (size_t)(DEPTH - 1) * W * ldh;
   static constexpr size_t ws0 = wdo + (size_t)kOutP * ldh;
   static constexpr size_t wso = ws0 + (SIGMA ? (size_t)W * ldx : 0);
-  static constexpr size_t sx = wso + (SIGMA ? (size_t)kOutP * ldh : 0);
-  static constexpr size_t sh = sx + (size_t)kTile * ldx;
-  static constexpr size_t sg = sh + (size_t)DEPTH * kTile * ldh;
-  static constexpr size_t ssx = sg + (size_t)kTile * ldg;
-  static constexpr size_t ssh = ssx + (SIGMA ? (size_t)kTile * ldx : 0);
-  static constexpr size_t halves = ssh + (SIGMA ? (size_t)kTile * ldh : 0);
-  static constexpr size_t f_base = (halves * 2 + 15) / 16 * 16;  // bytes
-  // fp32 region (offsets in floats)
-  static constexpr size_t fdx = 0;                                // [256][33] dL/d(features)
-  static constexpr size_t fz0 = fdx + (size_t)kTile * kLddx;      // z0 / later dz0
-  static constexpr size_t flv = fz0 + kTile;                      // log_var / later dlv
-  static constexpr size_t frho = flv + kTile;
-  static constexpr size_t fxw = frho + kTile;                     // [256][3]
-  static constexpr size_t fred = fxw + 3 * kTile;                 // [8][16] warp partials
-  static constexpr size_t flt = fred + kNW * 16;                  // LevelTable
-  static constexpr size_t floats = flt + (sizeof(LevelTable) + 3) / 4;
-  static constexpr size_t bytes = f_base + floats * 4;
+  static constexpr size_t w_halves = wso + (SIGMA ? (size_t)kOutP * ldh : 0);
+  // ---- per-group fp16 tiles (offsets in halves from the group's base) ----
+  static constexpr size_t sx = 0;
+  static constexpr size_t sh = sx + (size_t)GR * ldx;
+  static constexpr size_t sg = sh + (size_t)DEPTH * GR * ldh;
+  static constexpr size_t ssx = sg + (size_t)GR * ldg;
+  static constexpr size_t ssh = ssx + (SIGMA ? (size_t)GR * ldx : 0);
+  static constexpr size_t g_halves = (ssh + (SIGMA ? (size_t)GR * ldh : 0) + 7) / 8 * 8;
+  // ---- per-group fp32 scratch (offsets in floats from the group's float base) ----
+  static constexpr size_t fz0 = 0;                       // z0, later dz0
+  static constexpr size_t flv = fz0 + GR;                // log_var
+  static constexpr size_t frho = flv + GR;
+  static constexpr size_t fxw = frho + GR;               // [GR][3] world coords, later dL/dx rows
+  static constexpr size_t fred = fxw + 3 * GR;           // [GW][16] warp partials (GW = GR/16 warps)
+  static constexpr size_t fdx = fred + GW * 16;          // [GR][33] dL/d(features) unless aliased
+  static constexpr size_t g_floats = fdx + (alias_dx ? 0 : (size_t)GR * kLddx);
+  // ---- CTA-shared fp32: level table + weight-gradient accumulators (packed MLP layout) ----
+  static constexpr size_t n_density = (size_t)W * kIn + (size_t)(DEPTH - 1) * W * W + (size_t)kOutP * W;
+  static constexpr size_t n_sigma = SIGMA ? ((size_t)W * kIn + (size_t)kOutP * W) : 0;
+  static constexpr size_t lt_floats = (sizeof(LevelTable) + 3) / 4;
+  // ---- byte offsets ----
+  static constexpr size_t b_groups = (w_halves * 2 + 15) / 16 * 16;
+  static constexpr size_t b_gfloats = b_groups + (size_t)NG * g_halves * 2;
+  static constexpr size_t b_lt = b_gfloats + (size_t)NG * g_floats * 4;
+  static constexpr size_t b_acc = b_lt + lt_floats * 4;
+  static constexpr size_t bytes = b_acc + (n_density + n_sigma) * 4;
+};
+
+template <int W, int DEPTH>
+struct RenderLayout {
+  static constexpr int ldx = kIn + kPad, ldh = W + kPad;
+  static constexpr size_t wd0 = 0;
+  static constexpr size_t wdh = wd0 + (size_t)W * ldx;
+  static constexpr size_t wdo = wdh + (size_t)(DEPTH - 1) * W * ldh;
+  static constexpr size_t sx = wdo + (size_t)kOutP * ldh;
+  static constexpr size_t halves = sx + (size_t)kTile * ldx;
+  static constexpr size_t f_base = (halves * 2 + 15) / 16 * 16;
+  static constexpr size_t fz0 = 0;
+  static constexpr size_t flt = fz0 + kTile;
+  static constexpr size_t bytes = f_base + (flt + (sizeof(LevelTable) + 3) / 4) * 4;
 };
 
 // ---- Philox4x32-10 + Box-Muller: three N(0,1) per (seed, sample index) ----
@@ -125,128 +157,123 @@ __device__ __forceinline__ LevelGeom level_from(const LevelTable& t, int l) {
   g.hashed = t.hashed[l];
   return g;
 }
-// vertex index with the (rarely needed) dense wrap-around kept off the fast path
-__device__ __forceinline__ uint32_t vertex_index_fast(const LevelGeom& lv, uint32_t cx, uint32_t cy, uint32_t cz) {
+// The 4 (y,z) corner entries of one lane (x-corner fixed): e[q], q = yb + 2 zb, level offset included.
+// The hashed / dense decision is warp-uniform and made once per level; corners are derived
+// incrementally (hash: two multiplies + XORs; dense: one base index + strides).
+__device__ __forceinline__ void corner_entries(const LevelGeom& lv, uint32_t cx, uint32_t gy, uint32_t gz, uint32_t e[4]) {
   if (lv.hashed) {
-    const uint32_t idx = cx ^ (cy * 2654435761u) ^ (cz * 805459861u);
-    return ((lv.size & (lv.size - 1)) == 0) ? (idx & (lv.size - 1)) : (idx % lv.size);
+    const uint32_t hy0 = gy * 2654435761u, hy1 = hy0 + 2654435761u;
+    const uint32_t hz0 = gz * 805459861u, hz1 = hz0 + 805459861u;
+    e[0] = cx ^ hy0 ^ hz0;
+    e[1] = cx ^ hy1 ^ hz0;
+    e[2] = cx ^ hy0 ^ hz1;
+    e[3] = cx ^ hy1 ^ hz1;
+    if ((lv.size & (lv.size - 1)) == 0) {
+      const uint32_t mask = lv.size - 1;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) e[q] = (e[q] & mask) + lv.offset;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) e[q] = e[q] % lv.size + lv.offset;
+    }
+  } else {
+    const uint32_t sy = lv.res, sz = lv.res * lv.res;
+    e[0] = cx + gy * sy + gz * sz;
+    e[1] = e[0] + sy;
+    e[2] = e[0] + sz;
+    e[3] = e[2] + sy;
+    if (e[3] >= lv.size || e[0] > e[3]) {  // wrap-around only for out-of-box samples (tcnn semantics: mod T_l)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) e[q] %= lv.size;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) e[q] += lv.offset;
   }
-  uint32_t idx = cx + cy * lv.res + cz * (lv.res * lv.res);
-  if (idx >= lv.size) idx %= lv.size;
-  return idx;
 }
 
-// Lane mapping of the gather / scatter phases.  A warp owns 32 samples and walks them in two
-// batches of 16; inside a batch lane = (sample s = lane >> 1, x-corner xb = lane & 1).  The two
-// x-neighbours of a cell are adjacent table entries (dense levels always, hashed levels whenever
-// g_x is even), so the two lanes of a pair hit the same 128-byte line and a warp-wide LDG / RED
-// touches <= 16 lines instead of 32 -- the L1 wavefront count, which bounds this kernel, halves.
-// Each lane blends / scatters its 4 (y,z) corners; one shfl_xor(1) combines the pair.
+// Lane mapping of the whole kernel: a warp owns 16 samples, lane = (sample s = lane >> 1, x-corner
+// xb = lane & 1); both lanes of a pair carry the sample's geometry.  The two x-neighbours of a grid
+// cell are adjacent table entries (dense levels always, hashed levels whenever g_x is even), so the
+// two lanes of a pair hit the same 128-byte line and a warp-wide LDG / RED touches <= 16 lines
+// instead of 32 -- the L1 wavefront count, which bounds the gather / scatter phases, halves.  Each
+// lane blends / scatters its 4 (y,z) corners; one shfl_xor(1) combines the pair.
 
-// ---- phase 0: encode the warp's 32 samples into their fp16 rows of the shared tile ----
+// ---- phase 0: encode the warp's 16 samples into their fp16 rows of the shared tile ----
 __device__ __forceinline__ void encode_warp(const float xn[3], const LevelTable& lt, int n_levels, const __half* __restrict__ table,
                                             __half* rows /* first row of this warp */, int ld) {
   const int lane = threadIdx.x & 31, xb = lane & 1, sl = lane >> 1;
-  float px[2][3];
-#pragma unroll
-  for (int b = 0; b < 2; ++b)
-#pragma unroll
-    for (int d = 0; d < 3; ++d) px[b][d] = __shfl_sync(0xffffffffu, xn[d], b * 16 + sl);
-#pragma unroll 2
+  __half* row = rows + (size_t)sl * ld;
+#pragma unroll 4
   for (int l = 0; l < n_levels; ++l) {
     const LevelGeom lv = level_from(lt, l);
-    float2 f[2][4];
-    float wq[2][4];
+    uint32_t g[3], e[4];
+    float w[3];
+    level_pos(xn, lv.scale, g, w);
+    corner_entries(lv, g[0] + xb, g[1], g[2], e);
+    float2 f[4];
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      uint32_t g[3];
-      float w[3];
-      level_pos(px[b], lv.scale, g, w);
-      const float wx = xb ? w[0] : 1.f - w[0];
+    for (int q = 0; q < 4; ++q) f[q] = load_pair(table, e[q]);
+    const float wx = xb ? w[0] : 1.f - w[0];
+    const float wy0 = wx * (1.f - w[1]), wy1 = wx * w[1];
+    const float wq[4] = {wy0 * (1.f - w[2]), wy1 * (1.f - w[2]), wy0 * w[2], wy1 * w[2]};
+    float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t e = lv.offset + vertex_index_fast(lv, g[0] + xb, g[1] + (q & 1), g[2] + (q >> 1));
-        f[b][q] = load_pair(table, e);
-        wq[b][q] = wx * ((q & 1) ? w[1] : 1.f - w[1]) * ((q >> 1) ? w[2] : 1.f - w[2]);
-      }
+    for (int q = 0; q < 4; ++q) {
+      a0 = fmaf(wq[q], f[q].x, a0);
+      a1 = fmaf(wq[q], f[q].y, a1);
     }
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        a0 = fmaf(wq[b][q], f[b][q].x, a0);
-        a1 = fmaf(wq[b][q], f[b][q].y, a1);
-      }
-      a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-      if (xb == 0) *reinterpret_cast<__half2*>(rows + (size_t)(b * 16 + sl) * ld + 2 * l) = __floats2half2_rn(a0, a1);
-    }
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+    if (xb == 0) *reinterpret_cast<__half2*>(row + 2 * l) = __floats2half2_rn(a0, a1);
   }
-  // zero the padding columns of this thread's own row
-  for (int l = n_levels; l < kIn / 2; ++l) *reinterpret_cast<uint32_t*>(rows + (size_t)lane * ld + 2 * l) = 0u;
+  // zero the padding columns (the pair splits them)
+  for (int l = n_levels + xb; l < kIn / 2; l += 2) *reinterpret_cast<uint32_t*>(row + 2 * l) = 0u;
 }
 
-// ---- phase 3 tail: scatter dL/d(features) of the warp's 32 samples; optionally dL/dx through the grid ----
-// grows: fp32 [32][kLddx] rows of this warp; gxs: fp32 [32][3] output rows (only when kInputGrad)
+// ---- phase 3 tail: scatter dL/d(features) of the warp's 16 samples; optionally dL/dx through the grid ----
+// grows: fp32 [16][kLddx] rows of this warp; gx: dL/dx_normalised of this lane's sample (both lanes of a pair)
 template <bool kInputGrad>
 __device__ __forceinline__ void scatter_warp(const float xn[3], const LevelTable& lt, int n_levels, const __half* __restrict__ table,
-                                             const float* grows, float inv_scale, float* __restrict__ g_table, float* gxs) {
+                                             const float* grows, float inv_scale, float* __restrict__ g_table, float gx[3]) {
   const int lane = threadIdx.x & 31, xb = lane & 1, sl = lane >> 1;
-  float px[2][3];
-#pragma unroll
-  for (int b = 0; b < 2; ++b)
-#pragma unroll
-    for (int d = 0; d < 3; ++d) px[b][d] = __shfl_sync(0xffffffffu, xn[d], b * 16 + sl);
-  float gx[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-#pragma unroll 2
+  const float* gr = grows + (size_t)sl * kLddx;
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll 4
   for (int l = 0; l < n_levels; ++l) {
     const LevelGeom lv = level_from(lt, l);
+    const float g0 = gr[2 * l] * inv_scale, g1 = gr[2 * l + 1] * inv_scale;
+    uint32_t g[3], e[4];
+    float w[3];
+    level_pos(xn, lv.scale, g, w);
+    corner_entries(lv, g[0] + xb, g[1], g[2], e);
+    const float wx = xb ? w[0] : 1.f - w[0];
+    if (kInputGrad) {
+      float2 f[4];
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const float* gr = grows + (size_t)(b * 16 + sl) * kLddx + 2 * l;
-      const float g0 = gr[0] * inv_scale, g1 = gr[1] * inv_scale;
-      uint32_t g[3];
-      float w[3];
-      level_pos(px[b], lv.scale, g, w);
-      const float wx = xb ? w[0] : 1.f - w[0];
-      uint32_t e[4];
+      for (int q = 0; q < 4; ++q) f[q] = load_pair(table, e[q]);
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) e[q] = lv.offset + vertex_index_fast(lv, g[0] + xb, g[1] + (q & 1), g[2] + (q >> 1));
-      if (kInputGrad) {
-        float2 f[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) f[q] = load_pair(table, e[q]);
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float dot = fmaf(f[q].x, g0, f[q].y * g1);
-          const float fy = (q & 1) ? w[1] : 1.f - w[1], fz = (q >> 1) ? w[2] : 1.f - w[2];
-          d0 += (xb ? dot : -dot) * fy * fz;
-          d1 += ((q & 1) ? dot : -dot) * wx * fz;
-          d2 += ((q >> 1) ? dot : -dot) * wx * fy;
-        }
-        gx[b][0] = fmaf(lv.scale, d0, gx[b][0]);
-        gx[b][1] = fmaf(lv.scale, d1, gx[b][1]);
-        gx[b][2] = fmaf(lv.scale, d2, gx[b][2]);
+      for (int q = 0; q < 4; ++q) {
+        const float dot = fmaf(f[q].x, g0, f[q].y * g1);
+        const float fy = (q & 1) ? w[1] : 1.f - w[1], fz = (q >> 1) ? w[2] : 1.f - w[2];
+        d0 += (xb ? dot : -dot) * fy * fz;
+        d1 += ((q & 1) ? dot : -dot) * wx * fz;
+        d2 += ((q >> 1) ? dot : -dot) * wx * fy;
       }
-      if (g0 != 0.f || g1 != 0.f) {
+      acc[0] = fmaf(lv.scale, d0, acc[0]);
+      acc[1] = fmaf(lv.scale, d1, acc[1]);
+      acc[2] = fmaf(lv.scale, d2, acc[2]);
+    }
+    if (g0 != 0.f || g1 != 0.f) {
+      const float wy0 = wx * (1.f - w[1]), wy1 = wx * w[1];
+      const float wt[4] = {wy0 * (1.f - w[2]), wy1 * (1.f - w[2]), wy0 * w[2], wy1 * w[2]};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float wt = wx * ((q & 1) ? w[1] : 1.f - w[1]) * ((q >> 1) ? w[2] : 1.f - w[2]);
-          red_add_v2(g_table + 2 * (size_t)e[q], wt * g0, wt * g1);
-        }
-      }
+      for (int q = 0; q < 4; ++q) red_add_v2(g_table + 2 * (size_t)e[q], wt[q] * g0, wt[q] * g1);
     }
   }
   if (kInputGrad) {
 #pragma unroll
-    for (int b = 0; b < 2; ++b)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const float v = gx[b][d] + __shfl_xor_sync(0xffffffffu, gx[b][d], 1);
-        if (xb == 0) gxs[(size_t)(b * 16 + sl) * 3 + d] = v;
-      }
+    for (int d = 0; d < 3; ++d) gx[d] = acc[d] + __shfl_xor_sync(0xffffffffu, acc[d], 1);
   }
 }
 
@@ -254,86 +281,114 @@ __device__ __forceinline__ float softplus_f(float z) { return z > 20.f ? z : log
 __device__ __forceinline__ float sigmoid_f(float z) { return 1.f / (1.f + expf(-z)); }
 
 // column 0 of a 2-n-tile accumulator -> per-row scalar array (rows of this warp)
-__device__ __forceinline__ void store_col0(const float (&c)[2][2][4], float* dst, int row0) {
+template <int MTL>
+__device__ __forceinline__ void store_col0(const float (&c)[MTL][2][4], float* dst, int row0) {
   const int lane = threadIdx.x & 31;
   if ((lane & 3) == 0) {
     const int g = lane >> 2;
 #pragma unroll
-    for (int m = 0; m < 2; ++m) {
+    for (int m = 0; m < MTL; ++m) {
       dst[row0 + m * 16 + g] = c[m][0][0];
       dst[row0 + m * 16 + g + 8] = c[m][0][2];
     }
   }
 }
 
-template <int W, int DEPTH, bool SIGMA>
-__global__ void __launch_bounds__(kTile, 1) inr_train_kernel(const __grid_constant__ FusedArgs a) {
-  using L = Layout<W, DEPTH, SIGMA>;
+__device__ __forceinline__ void group_barrier(int grp, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void red_shared(float* p, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_u32(p)), "f"(v) : "memory");
+}
+
+// add a warp's freshly computed dW block into the CTA's shared fp32 accumulator (row-major [OUT][IN])
+template <int OUT, int IN, int NW>
+__device__ __forceinline__ void wgrad_to_smem(const float (&acc)[WgradSplit<OUT, IN, NW>::NTW][4], float* sacc, int warp_in_group) {
+  using S = WgradSplit<OUT, IN, NW>;
+  const int lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+  const int mt = warp_in_group % S::MT, part = warp_in_group / S::MT;
+  if (part >= S::PARTS) return;
+#pragma unroll
+  for (int j = 0; j < S::NTW; ++j) {
+    const int nt = part * S::NTW + j;
+    if (nt >= S::NTL) continue;
+    float* p = sacc + (size_t)(mt * 16 + gq) * IN + nt * 8 + 2 * t;
+    red_shared(p, acc[j][0]);
+    red_shared(p + 1, acc[j][1]);
+    red_shared(p + 8 * IN, acc[j][2]);
+    red_shared(p + 8 * IN + 1, acc[j][3]);
+  }
+}
+
+// one layer's weight gradient for this group's tile: registers -> shared accumulator
+template <int OUT, int IN, int NW>
+__device__ __forceinline__ void group_wgrad(float* sacc, const __half* dc_tile, int ld_dc, const __half* a_tile, int ld_a, int rows,
+                                            int warp_in_group) {
+  float acc[WgradSplit<OUT, IN, NW>::NTW][4] = {};
+  warp_wgrad<OUT, IN, NW>(acc, dc_tile, ld_dc, a_tile, ld_a, rows, warp_in_group);
+  wgrad_to_smem<OUT, IN, NW>(acc, sacc, warp_in_group);
+}
+
+template <int W, int DEPTH, bool SIGMA, int GR>
+__global__ void __launch_bounds__(kThreads, 1) inr_train_kernel(const __grid_constant__ FusedArgs a) {
+  using L = Layout<W, DEPTH, SIGMA, GR>;
+  constexpr int GW = L::GW, NG = L::NG, GT = GR * 2;  // warps / threads per group
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __half* sh = reinterpret_cast<__half*>(smem_raw);
-  float* sf = reinterpret_cast<float*>(smem_raw + L::f_base);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row0 = warp * 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = warp / GW, gw = warp % GW, row0 = gw * 16;
+  const int xb = lane & 1, srow = row0 + (lane >> 1);  // this lane's sample row inside the group tile
+  __half* swt = reinterpret_cast<__half*>(smem_raw);                                           // weights
+  __half* sh = reinterpret_cast<__half*>(smem_raw + L::b_groups) + (size_t)grp * L::g_halves;  // this group's tiles
+  float* sf = reinterpret_cast<float*>(smem_raw + L::b_gfloats) + (size_t)grp * L::g_floats;
+  LevelTable& lt = *reinterpret_cast<LevelTable*>(smem_raw + L::b_lt);
+  float* sacc = reinterpret_cast<float*>(smem_raw + L::b_acc);
+  float* sacc_sigma = sacc + L::n_density;
   const nsv_inr_config& cfg = a.cfg;
 
-  // ---- stage weights (fp16, padded rows) ----
+  // ---- stage weights (fp16, padded rows), level table; clear the gradient accumulators ----
   {
     const __half* wd = a.mlp + a.off_density;
-    stage_weights(sh + L::wd0, L::ldx, wd, W, kIn);
-    for (int l = 0; l + 1 < DEPTH; ++l) stage_weights(sh + L::wdh + (size_t)l * W * L::ldh, L::ldh, wd + (size_t)W * kIn + (size_t)l * W * W, W, W);
-    stage_weights(sh + L::wdo, L::ldh, wd + (size_t)W * kIn + (size_t)(DEPTH - 1) * W * W, kOutP, W);
+    stage_weights(swt + L::wd0, L::ldx, wd, W, kIn);
+    for (int l = 0; l + 1 < DEPTH; ++l) stage_weights(swt + L::wdh + (size_t)l * W * L::ldh, L::ldh, wd + (size_t)W * kIn + (size_t)l * W * W, W, W);
+    stage_weights(swt + L::wdo, L::ldh, wd + (size_t)W * kIn + (size_t)(DEPTH - 1) * W * W, kOutP, W);
     if (SIGMA) {
       const __half* ws = a.mlp + a.off_sigma;
-      stage_weights(sh + L::ws0, L::ldx, ws, W, kIn);
-      stage_weights(sh + L::wso, L::ldh, ws + (size_t)W * kIn, kOutP, W);
+      stage_weights(swt + L::ws0, L::ldx, ws, W, kIn);
+      stage_weights(swt + L::wso, L::ldh, ws + (size_t)W * kIn, kOutP, W);
+    }
+    for (int i = tid; i < (int)(L::n_density + L::n_sigma); i += kThreads) sacc[i] = 0.f;
+    if (tid < kIn / 2) {
+      lt.scale[tid] = cfg.grid.scale[tid];
+      lt.res[tid] = cfg.grid.res[tid];
+      lt.size[tid] = cfg.grid.size[tid];
+      lt.offset[tid] = cfg.grid.offset[tid];
+      lt.hashed[tid] = cfg.grid.hashed[tid];
     }
   }
-  LevelTable& lt = *reinterpret_cast<LevelTable*>(sf + L::flt);
-  if (tid < kIn / 2) {
-    lt.scale[tid] = cfg.grid.scale[tid];
-    lt.res[tid] = cfg.grid.res[tid];
-    lt.size[tid] = cfg.grid.size[tid];
-    lt.offset[tid] = cfg.grid.offset[tid];
-    lt.hashed[tid] = cfg.grid.hashed[tid];
-  }
-  // ---- log-sum-exp of logit_coef (slice scale c_k = n_s softmax_k) ----
+  // ---- log-sum-exp of logit_coef (slice scale c_k = n_s softmax_k), per warp (n_slices is small) ----
   float lse = 0.f;
   if (cfg.slice_scale) {
     float mx = -INFINITY;
-    for (int k = tid; k < a.n_slices; k += kTile) mx = fmaxf(mx, a.logit_coef[k]);
+    for (int k = lane; k < a.n_slices; k += 32) mx = fmaxf(mx, a.logit_coef[k]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) sf[L::fred + warp] = mx;
-    __syncthreads();
-    mx = sf[L::fred];
-    for (int k = 1; k < kNW; ++k) mx = fmaxf(mx, sf[L::fred + k]);
-    __syncthreads();
     float se = 0.f;
-    for (int k = tid; k < a.n_slices; k += kTile) se += expf(a.logit_coef[k] - mx);
+    for (int k = lane; k < a.n_slices; k += 32) se += expf(a.logit_coef[k] - mx);
     se = warp_sum(se);
-    if (lane == 0) sf[L::fred + warp] = se;
-    __syncthreads();
-    se = 0.f;
-    for (int k = 0; k < kNW; ++k) se += sf[L::fred + k];
     lse = mx + logf(se);
   }
   __syncthreads();
 
-  // weight-gradient accumulators (registers, persistent across tiles)
-  float acc_d0[WgradSplit<W, kIn, kNW>::NTW][4] = {};
-  float acc_dh[DEPTH > 1 ? DEPTH - 1 : 1][WgradSplit<W, W, kNW>::NTW][4] = {};
-  float acc_do[WgradSplit<kOutP, W, kNW>::NTW][4] = {};
-  float acc_s0[WgradSplit<W, kIn, kNW>::NTW][4] = {};
-  float acc_so[WgradSplit<kOutP, W, kNW>::NTW][4] = {};
   float loss_d = 0.f, loss_s = 0.f, loss_i = 0.f;
-
-  const int S = a.S, wpp = S >> 5;  // warps per pixel
+  const int S = a.S, wpp = S >> 4;  // warps per pixel
   const float invS = 1.f / (float)S, invB = 1.f / (float)a.B, gscale = cfg.grad_scale, inv_gscale = 1.f / cfg.grad_scale;
-  const int64_t n_tiles = (a.B * (int64_t)S) / kTile;
+  const int64_t n_tiles = (a.B * (int64_t)S) / GR;
 
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    __syncthreads();  // previous tile's cooperative wgrad reads are complete
+  for (int64_t tile = (int64_t)blockIdx.x * NG + grp; tile < n_tiles; tile += (int64_t)gridDim.x * NG) {
+    group_barrier(grp, GT);  // previous tile's cooperative wgrad reads of this group's tiles are complete
     // ================= phase 0: sample geometry + encoding =================
-    const int64_t sidx = tile * kTile + tid;
+    const int64_t sidx = tile * GR + srow;
     const int64_t p = sidx >> a.log2S;
     const int j = (int)(sidx & (S - 1));
     const int k = (int)a.slice_idx[p];
@@ -360,68 +415,74 @@ __global__ void __launch_bounds__(kTile, 1) inr_train_kernel(const __grid_consta
     encode_warp(xn, lt, cfg.grid.n_levels, a.table, sh + L::sx + (size_t)row0 * L::ldx, L::ldx);
     __syncwarp();
 
-    // ================= phase 1: density MLP forward (warp-local) =================
-    uint32_t az[2][1][4];  // z0..z15 as an A fragment (input of sigma_net)
+    // ================= phase 1: density MLP forward (warp-local, one m16 tile per warp) =================
+    uint32_t az[1][1][4];  // z0..z15 as an A fragment (input of sigma_net)
+    uint64_t relu_mask[DEPTH], relu_mask_s = 0;  // pre-activation > 0 bits of this thread's fragment elements
     {
-      uint32_t ain[2][kIn / 16][4];
+      uint32_t ain[1][kIn / 16][4];
       load_a_frags<kIn / 16>(ain, sh + L::sx, L::ldx, row0);
-      float c[2][W / 8][4];
-      warp_gemm_fwd<kIn / 16, W / 8>(c, ain, sh + L::wd0, L::ldx);
-      uint32_t ah[2][W / 16][4];
+      float c[1][W / 8][4];
+      warp_gemm_fwd<kIn / 16, W / 8>(c, ain, swt + L::wd0, L::ldx);
+      uint32_t ah[1][W / 16][4];
+      relu_mask[0] = relu_bits<W / 8>(c);
       acc_to_a<W / 8, true>(ah, c);
       store_a_frags<W / 16>(ah, sh + L::sh, L::ldh, row0);
 #pragma unroll
       for (int l = 1; l < DEPTH; ++l) {
-        warp_gemm_fwd<W / 16, W / 8>(c, ah, sh + L::wdh + (size_t)(l - 1) * W * L::ldh, L::ldh);
+        warp_gemm_fwd<W / 16, W / 8>(c, ah, swt + L::wdh + (size_t)(l - 1) * W * L::ldh, L::ldh);
+        relu_mask[l] = relu_bits<W / 8>(c);
         acc_to_a<W / 8, true>(ah, c);
-        store_a_frags<W / 16>(ah, sh + L::sh + (size_t)l * kTile * L::ldh, L::ldh, row0);
+        store_a_frags<W / 16>(ah, sh + L::sh + (size_t)l * GR * L::ldh, L::ldh, row0);
       }
-      float co[2][2][4];
-      warp_gemm_fwd<W / 16, 2>(co, ah, sh + L::wdo, L::ldh);
+      float co[1][2][4];
+      warp_gemm_fwd<W / 16, 2>(co, ah, swt + L::wdo, L::ldh);
       store_col0(co, sf + L::fz0, row0);
       acc_to_a<2, false>(az, co);
     }
     // ================= phase 1b: sigma MLP forward =================
     if (SIGMA) {
-      __half* srow = sh + L::ssx + (size_t)tid * L::ldx;  // [slice embedding (16) | z (16)]
-      const float* se = a.slice_embedding + (size_t)k * 16;
+      __half* sr = sh + L::ssx + (size_t)srow * L::ldx + 8 * xb;  // [slice embedding (16) | z (16)], 8 halves per lane
+      const float* se = a.slice_embedding + (size_t)k * 16 + 8 * xb;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) *reinterpret_cast<__half2*>(srow + 2 * q) = __floats2half2_rn(se[2 * q], se[2 * q + 1]);
+      for (int q = 0; q < 4; ++q) *reinterpret_cast<__half2*>(sr + 2 * q) = __floats2half2_rn(se[2 * q], se[2 * q + 1]);
       store_a_frags<1>(az, sh + L::ssx + 16, L::ldx, row0);
       __syncwarp();
-      uint32_t asx[2][2][4];
+      uint32_t asx[1][2][4];
       load_a_frags<2>(asx, sh + L::ssx, L::ldx, row0);
-      float c[2][W / 8][4];
-      warp_gemm_fwd<2, W / 8>(c, asx, sh + L::ws0, L::ldx);
-      uint32_t ash[2][W / 16][4];
+      float c[1][W / 8][4];
+      warp_gemm_fwd<2, W / 8>(c, asx, swt + L::ws0, L::ldx);
+      uint32_t ash[1][W / 16][4];
+      relu_mask_s = relu_bits<W / 8>(c);
       acc_to_a<W / 8, true>(ash, c);
       store_a_frags<W / 16>(ash, sh + L::ssh, L::ldh, row0);
-      float co[2][2][4];
-      warp_gemm_fwd<W / 16, 2>(co, ash, sh + L::wso, L::ldh);
+      float co[1][2][4];
+      warp_gemm_fwd<W / 16, 2>(co, ash, swt + L::wso, L::ldh);
       store_col0(co, sf + L::flv, row0);
     }
     __syncwarp();
 
-    // ================= phase 2: render, losses, gradients w.r.t. z0 / log_var =================
-    const float z0 = sf[L::fz0 + tid];
+    // ================= phase 2: render, losses, gradients w.r.t. z0 / log_var (both lanes of a pair) =================
+    const float z0 = sf[L::fz0 + srow];
     const float rho = softplus_f(z0);
-    const float lv = SIGMA ? sf[L::flv + tid] : 0.f;
+    const float lv = SIGMA ? sf[L::flv + srow] : 0.f;
     const float u = SIGMA ? expf(lv) : 1.f;
-    sf[L::frho + tid] = rho;
-    sf[L::fxw + 3 * tid] = xw[0];
-    sf[L::fxw + 3 * tid + 1] = xw[1];
-    sf[L::fxw + 3 * tid + 2] = xw[2];
+    if (xb == 0) {
+      sf[L::frho + srow] = rho;
+      sf[L::fxw + 3 * srow] = xw[0];
+      sf[L::fxw + 3 * srow + 1] = xw[1];
+      sf[L::fxw + 3 * srow + 2] = xw[2];
+    }
     {
-      const float s_rho = warp_sum(rho), s_u = warp_sum(u);
+      const float s_rho = warp_sum(xb ? 0.f : rho), s_u = warp_sum(xb ? 0.f : u);
       if (lane == 0) {
-        sf[L::fred + warp * 2] = s_rho;
-        sf[L::fred + warp * 2 + 1] = s_u;
+        sf[L::fred + gw * 2] = s_rho;
+        sf[L::fred + gw * 2 + 1] = s_u;
       }
     }
-    __syncthreads();
+    group_barrier(grp, GT);
     float m_pix = 0.f, q_pix = 0.f;
     {
-      const int w0 = (warp / wpp) * wpp;
+      const int w0 = (gw / wpp) * wpp;
       for (int q = 0; q < wpp; ++q) {
         m_pix += sf[L::fred + (w0 + q) * 2];
         q_pix += sf[L::fred + (w0 + q) * 2 + 1];
@@ -440,7 +501,7 @@ __global__ void __launch_bounds__(kTile, 1) inr_train_kernel(const __grid_consta
     const float d_var = (SIGMA || cfg.slice_variance) ? (0.5f / var - 0.5f * e * e / (var * var)) * invB : 0.f;
     float d_rho = ck * d_vhat * invS;
     const float d_lv = SIGMA ? (u * invS) * ck * 2.f * r * d_var : 0.f;
-    if (j == 0) {
+    if (j == 0 && xb == 0) {
       loss_d += 0.5f * e * e / var * invB;
       if (SIGMA || cfg.slice_variance) loss_s += 0.5f * logf(var) * invB;
       if (a.v_out) a.v_out[p] = vhat;
@@ -448,61 +509,64 @@ __global__ void __launch_bounds__(kTile, 1) inr_train_kernel(const __grid_consta
       if (cfg.slice_variance) red_add(a.g_lvs + k, evs * d_var);
     }
     if (cfg.image_reg) {
-      const int tp = (tid & ~(S - 1)) + (S - 1 - j);
+      const int tp = (srow & ~(S - 1)) + (S - 1 - j);
       const float dr = rho - sf[L::frho + tp];
       const float dx0 = xw[0] - sf[L::fxw + 3 * tp], dx1 = xw[1] - sf[L::fxw + 3 * tp + 1], dx2 = xw[2] - sf[L::fxw + 3 * tp + 2];
       const float d2 = dx0 * dx0 + dx1 * dx1 + dx2 * dx2 + 1e-6f;
       const float nbs = invB * invS;
+      float li;
       if (cfg.image_reg == 2) {  // edge
         const float sq = sqrtf(1.f + dr * dr / (d2 * cfg.delta * cfg.delta));
-        loss_i += sq * nbs;
+        li = sq * nbs;
         d_rho += cfg.w_image * 2.f * dr / (cfg.delta * d2 * sq) * nbs;
       } else if (cfg.image_reg == 1) {  // TV
         const float dd = sqrtf(d2);
-        loss_i += fabsf(dr) / dd * nbs;
+        li = fabsf(dr) / dd * nbs;
         d_rho += cfg.w_image * 2.f * (dr > 0.f ? 1.f : (dr < 0.f ? -1.f : 0.f)) / dd * nbs;
       } else {  // L2
-        loss_i += dr * dr / d2 * nbs;
+        li = dr * dr / d2 * nbs;
         d_rho += cfg.w_image * 4.f * dr / d2 * nbs;
       }
+      if (xb == 0) loss_i += li;
     }
     const float dz0 = (z0 > 20.f ? 1.f : sigmoid_f(z0)) * d_rho * gscale;
-    sf[L::fz0 + tid] = dz0;  // own slot: z0 is dead
-    if (SIGMA) {
-      __half* grow = sh + L::sg + (size_t)tid * L::ldg;
-      *reinterpret_cast<uint4*>(grow) = make_uint4((uint32_t)__half_as_ushort(__float2half_rn(d_lv * gscale)), 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(grow + 8) = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();  // both lanes of every pair have read z0
+    if (xb == 0) {
+      sf[L::fz0 + srow] = dz0;  // z0 is dead
+      if (SIGMA) {
+        __half* grow = sh + L::sg + (size_t)srow * L::ldg;
+        *reinterpret_cast<uint4*>(grow) = make_uint4((uint32_t)__half_as_ushort(__float2half_rn(d_lv * gscale)), 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(grow + 8) = make_uint4(0u, 0u, 0u, 0u);
+      }
     }
-    __syncthreads();  // [B0] sG / activations of every warp are in place
+    group_barrier(grp, GT);  // [B0] sG / activations of every warp of the group are in place
 
     // ================= phase 3: backward =================
-    float c2[2][2][4];  // dL/dz (16 columns) of the density net, fp32 fragment
+    float c2[1][2][4];  // dL/dz (16 columns) of the density net, fp32 fragment
 #pragma unroll
-    for (int m = 0; m < 2; ++m)
+    for (int n = 0; n < 2; ++n)
 #pragma unroll
-      for (int n = 0; n < 2; ++n)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) c2[m][n][q] = 0.f;
+      for (int q = 0; q < 4; ++q) c2[0][n][q] = 0.f;
     if (SIGMA) {
-      warp_wgrad<kOutP, W, kNW>(acc_so, sh + L::sg, L::ldg, sh + L::ssh, L::ldh, kTile);
-      uint32_t ag[2][1][4];
+      group_wgrad<kOutP, W, GW>(sacc_sigma + (size_t)W * kIn, sh + L::sg, L::ldg, sh + L::ssh, L::ldh, GR, gw);
+      uint32_t ag[1][1][4];
       load_a_frags<1>(ag, sh + L::sg, L::ldg, row0);
-      float c[2][W / 8][4];
-      warp_gemm_dgrad<1, W / 8>(c, ag, sh + L::wso, L::ldh);
-      relu_mask_acc<W / 8>(c, sh + L::ssh, L::ldh, row0);
-      uint32_t adz[2][W / 16][4];
+      float c[1][W / 8][4];
+      warp_gemm_dgrad<1, W / 8>(c, ag, swt + L::wso, L::ldh);
+      apply_relu_bits<W / 8>(c, relu_mask_s);
+      uint32_t adz[1][W / 16][4];
       acc_to_a<W / 8, false>(adz, c);
-      __syncthreads();  // [B1]
+      group_barrier(grp, GT);  // [B1]
       store_a_frags<W / 16>(adz, sh + L::ssh, L::ldh, row0);
-      __syncthreads();  // [B2]
-      warp_wgrad<W, kIn, kNW>(acc_s0, sh + L::ssh, L::ldh, sh + L::ssx, L::ldx, kTile);
-      float cin[2][4][4];
-      warp_gemm_dgrad<W / 16, 4>(cin, adz, sh + L::ws0, L::ldx);
-      // d(slice embedding): column sums over the warp's 32 rows (one pixel, one slice per warp)
+      group_barrier(grp, GT);  // [B2]
+      group_wgrad<W, kIn, GW>(sacc_sigma, sh + L::ssh, L::ldh, sh + L::ssx, L::ldx, GR, gw);
+      float cin[1][4][4];
+      warp_gemm_dgrad<W / 16, 4>(cin, adz, swt + L::ws0, L::ldx);
+      // d(slice embedding): column sums over the warp's 16 rows (one pixel, one slice per warp)
 #pragma unroll
       for (int n = 0; n < 2; ++n) {
-        float s0 = cin[0][n][0] + cin[0][n][2] + cin[1][n][0] + cin[1][n][2];
-        float s1 = cin[0][n][1] + cin[0][n][3] + cin[1][n][1] + cin[1][n][3];
+        float s0 = cin[0][n][0] + cin[0][n][2];
+        float s1 = cin[0][n][1] + cin[0][n][3];
 #pragma unroll
         for (int o = 4; o < 32; o <<= 1) {
           s0 += __shfl_xor_sync(0xffffffffu, s0, o);
@@ -511,98 +575,91 @@ __global__ void __launch_bounds__(kTile, 1) inr_train_kernel(const __grid_consta
         if (lane < 4) red_add_v2(a.g_se + (size_t)k * 16 + n * 8 + 2 * lane, s0 * inv_gscale, s1 * inv_gscale);
       }
 #pragma unroll
-      for (int m = 0; m < 2; ++m)
+      for (int n = 0; n < 2; ++n)
 #pragma unroll
-        for (int n = 0; n < 2; ++n)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) c2[m][n][q] = cin[m][2 + n][q];
+        for (int q = 0; q < 4; ++q) c2[0][n][q] = cin[0][2 + n][q];
     }
     if ((lane & 3) == 0) {  // add dL/dz0 of the render path to column 0
       const int g = lane >> 2;
-#pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        c2[m][0][0] += sf[L::fz0 + row0 + m * 16 + g];
-        c2[m][0][2] += sf[L::fz0 + row0 + m * 16 + g + 8];
-      }
+      c2[0][0][0] += sf[L::fz0 + row0 + g];
+      c2[0][0][2] += sf[L::fz0 + row0 + g + 8];
     }
-    uint32_t adz[2][W / 16][4];
+    uint32_t adz[1][W / 16][4];
     {
-      uint32_t ag[2][1][4];
+      uint32_t ag[1][1][4];
       acc_to_a<2, false>(ag, c2);
       store_a_frags<1>(ag, sh + L::sg, L::ldg, row0);  // sG is free: sigma's wgrad finished before [B1]
-      __syncthreads();  // [B3]
-      __half* sHl = sh + L::sh + (size_t)(DEPTH - 1) * kTile * L::ldh;
-      warp_wgrad<kOutP, W, kNW>(acc_do, sh + L::sg, L::ldg, sHl, L::ldh, kTile);
-      float c[2][W / 8][4];
-      warp_gemm_dgrad<1, W / 8>(c, ag, sh + L::wdo, L::ldh);
-      relu_mask_acc<W / 8>(c, sHl, L::ldh, row0);
+      group_barrier(grp, GT);  // [B3]
+      __half* sHl = sh + L::sh + (size_t)(DEPTH - 1) * GR * L::ldh;
+      group_wgrad<kOutP, W, GW>(sacc + (size_t)W * kIn + (size_t)(DEPTH - 1) * W * W, sh + L::sg, L::ldg, sHl, L::ldh, GR, gw);
+      float c[1][W / 8][4];
+      warp_gemm_dgrad<1, W / 8>(c, ag, swt + L::wdo, L::ldh);
+      apply_relu_bits<W / 8>(c, relu_mask[DEPTH - 1]);
       acc_to_a<W / 8, false>(adz, c);
-      __syncthreads();  // [B4]
+      group_barrier(grp, GT);  // [B4]
       store_a_frags<W / 16>(adz, sHl, L::ldh, row0);
-      __syncthreads();  // [B5]
+      group_barrier(grp, GT);  // [B5]
     }
 #pragma unroll
     for (int l = DEPTH - 1; l >= 1; --l) {
-      __half* sDz = sh + L::sh + (size_t)l * kTile * L::ldh;
-      __half* sHp = sh + L::sh + (size_t)(l - 1) * kTile * L::ldh;
-      warp_wgrad<W, W, kNW>(acc_dh[l - 1], sDz, L::ldh, sHp, L::ldh, kTile);
-      float c[2][W / 8][4];
-      warp_gemm_dgrad<W / 16, W / 8>(c, adz, sh + L::wdh + (size_t)(l - 1) * W * L::ldh, L::ldh);
-      relu_mask_acc<W / 8>(c, sHp, L::ldh, row0);
+      __half* sDz = sh + L::sh + (size_t)l * GR * L::ldh;
+      __half* sHp = sh + L::sh + (size_t)(l - 1) * GR * L::ldh;
+      group_wgrad<W, W, GW>(sacc + (size_t)W * kIn + (size_t)(l - 1) * W * W, sDz, L::ldh, sHp, L::ldh, GR, gw);
+      float c[1][W / 8][4];
+      warp_gemm_dgrad<W / 16, W / 8>(c, adz, swt + L::wdh + (size_t)(l - 1) * W * L::ldh, L::ldh);
+      apply_relu_bits<W / 8>(c, relu_mask[l - 1]);
       acc_to_a<W / 8, false>(adz, c);
-      __syncthreads();
+      group_barrier(grp, GT);
       store_a_frags<W / 16>(adz, sHp, L::ldh, row0);
-      __syncthreads();
+      group_barrier(grp, GT);
     }
-    warp_wgrad<W, kIn, kNW>(acc_d0, sh + L::sh, L::ldh, sh + L::sx, L::ldx, kTile);
+    group_wgrad<W, kIn, GW>(sacc, sh + L::sh, L::ldh, sh + L::sx, L::ldx, GR, gw);
+    // dL/d(features): fp32 rows, either in their own scratch or in the dead H_last slot (DEPTH >= 2:
+    // its last reader was the wgrad of layer DEPTH-1, two group barriers ago)
+    float* sdx = L::alias_dx ? reinterpret_cast<float*>(sh + L::sh + (size_t)(DEPTH - 1) * GR * L::ldh) : sf + L::fdx;
     {
-      float cx[2][kIn / 8][4];
-      warp_gemm_dgrad<W / 16, kIn / 8>(cx, adz, sh + L::wd0, L::ldx);
+      float cx[1][kIn / 8][4];
+      warp_gemm_dgrad<W / 16, kIn / 8>(cx, adz, swt + L::wd0, L::ldx);
       const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-      for (int m = 0; m < 2; ++m)
-#pragma unroll
-        for (int n = 0; n < kIn / 8; ++n) {
-          float* d0 = sf + L::fdx + (size_t)(row0 + m * 16 + g) * kLddx + n * 8 + 2 * t;
-          d0[0] = cx[m][n][0];
-          d0[1] = cx[m][n][1];
-          d0[8 * kLddx] = cx[m][n][2];
-          d0[8 * kLddx + 1] = cx[m][n][3];
-        }
+      for (int n = 0; n < kIn / 8; ++n) {
+        float* d0 = sdx + (size_t)(row0 + g) * kLddx + n * 8 + 2 * t;
+        d0[0] = cx[0][n][0];
+        d0[1] = cx[0][n][1];
+        d0[8 * kLddx] = cx[0][n][2];
+        d0[8 * kLddx + 1] = cx[0][n][3];
+      }
     }
     __syncwarp();
-    // ---- scatter into the table gradient (+ pose gradient), lanes = (sample, x-corner) ----
-    const float* grows = sf + L::fdx + (size_t)row0 * kLddx;
+    // ---- scatter into the table gradient (+ pose gradient) ----
+    const float* grows = sdx + (size_t)row0 * kLddx;
     if (cfg.pose_grad) {
-      float* gxs = sf + L::fxw + (size_t)row0 * 3;  // xw rows are dead after phase 2
-      scatter_warp<true>(xn, lt, cfg.grid.n_levels, a.table, grows, inv_gscale, a.g_table, gxs);
-      __syncwarp();
-      const float gx[3] = {gxs[lane * 3], gxs[lane * 3 + 1], gxs[lane * 3 + 2]};
-      float gw[3], part[12];
+      float gx[3];
+      scatter_warp<true>(xn, lt, cfg.grid.n_levels, a.table, grows, inv_gscale, a.g_table, gx);
+      float gwd[3], part[12];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) gw[i] = gx[i] / (cfg.bbox_hi[i] - cfg.bbox_lo[i]);
+      for (int i = 0; i < 3; ++i) gwd[i] = xb ? 0.f : gx[i] / (cfg.bbox_hi[i] - cfg.bbox_lo[i]);  // one lane per sample contributes
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int q = 0; q < 3; ++q) part[i * 3 + q] = gw[i] * y[q];  // dL/dR
+        for (int q = 0; q < 3; ++q) part[i * 3 + q] = gwd[i] * y[q];  // dL/dR
 #pragma unroll
-      for (int q = 0; q < 3; ++q) part[9 + q] = R[q] * gw[0] + R[3 + q] * gw[1] + R[6 + q] * gw[2];  // dL/dT = R^T g
+      for (int q = 0; q < 3; ++q) part[9 + q] = R[q] * gwd[0] + R[3 + q] * gwd[1] + R[6 + q] * gwd[2];  // dL/dT = R^T g
 #pragma unroll
       for (int q = 0; q < 12; ++q) part[q] = warp_sum(part[q]);
-      __syncthreads();  // fred is free again (phase-2 reads are long done), and all warps arrive here
+      group_barrier(grp, GT);  // fred is free again (phase-2 reads are long done)
       if (lane == 0) {
 #pragma unroll
-        for (int q = 0; q < 12; ++q) sf[L::fred + warp * 16 + q] = part[q];
+        for (int q = 0; q < 12; ++q) sf[L::fred + gw * 16 + q] = part[q];
       }
-      __syncthreads();
-      if (j == 0) {
+      group_barrier(grp, GT);
+      if (j == 0 && xb == 0) {
         float G[9], gT[3], gwv[3];
-        const int w0 = warp;  // first warp of this pixel
 #pragma unroll
         for (int q = 0; q < 12; ++q) {
-          float s = 0.f;
-          for (int ww = 0; ww < wpp; ++ww) s += sf[L::fred + (w0 + ww) * 16 + q];
-          if (q < 9) G[q] = s; else gT[q - 9] = s;
+          float sm = 0.f;
+          for (int ww = 0; ww < wpp; ++ww) sm += sf[L::fred + (gw + ww) * 16 + q];
+          if (q < 9) G[q] = sm; else gT[q - 9] = sm;
         }
         rodrigues_vjp<float>(ax, G, gwv);
 #pragma unroll
@@ -612,24 +669,22 @@ __global__ void __launch_bounds__(kTile, 1) inr_train_kernel(const __grid_consta
         }
       }
     } else {
-      scatter_warp<false>(xn, lt, cfg.grid.n_levels, a.table, grows, inv_gscale, a.g_table, nullptr);
+      float gx[3];
+      scatter_warp<false>(xn, lt, cfg.grid.n_levels, a.table, grows, inv_gscale, a.g_table, gx);
     }
   }
 
   // ================= epilogue: flush weight gradients and losses =================
-  {
-    float* gd = a.g_mlp + a.off_density;
-    flush_wgrad<W, kIn, kNW>(acc_d0, gd, kIn, inv_gscale);
-#pragma unroll
-    for (int l = 0; l + 1 < DEPTH; ++l) flush_wgrad<W, W, kNW>(acc_dh[l], gd + (size_t)W * kIn + (size_t)l * W * W, W, inv_gscale);
-    flush_wgrad<kOutP, W, kNW>(acc_do, gd + (size_t)W * kIn + (size_t)(DEPTH - 1) * W * W, W, inv_gscale);
-    if (SIGMA) {
-      float* gs = a.g_mlp + a.off_sigma;
-      flush_wgrad<W, kIn, kNW>(acc_s0, gs, kIn, inv_gscale);
-      flush_wgrad<kOutP, W, kNW>(acc_so, gs + (size_t)W * kIn, W, inv_gscale);
-    }
-  }
   __syncthreads();
+  for (int i = tid; i < (int)L::n_density; i += kThreads) {
+    const float v = sacc[i];
+    if (v != 0.f) red_add(a.g_mlp + a.off_density + i, v * inv_gscale);
+  }
+  if (SIGMA)
+    for (int i = tid; i < (int)L::n_sigma; i += kThreads) {
+      const float v = sacc_sigma[i];
+      if (v != 0.f) red_add(a.g_mlp + a.off_sigma + i, v * inv_gscale);
+    }
   loss_d = warp_sum(loss_d);
   loss_s = warp_sum(loss_s);
   loss_i = warp_sum(loss_i);
@@ -699,12 +754,13 @@ struct RenderArgs {
 };
 
 template <int W, int DEPTH>
-__global__ void __launch_bounds__(kTile, 1) inr_render_kernel(const __grid_constant__ RenderArgs a) {
-  using L = Layout<W, DEPTH, false>;
+__global__ void __launch_bounds__(kThreads, 1) inr_render_kernel(const __grid_constant__ RenderArgs a) {
+  using L = RenderLayout<W, DEPTH>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __half* sh = reinterpret_cast<__half*>(smem_raw);
   float* sf = reinterpret_cast<float*>(smem_raw + L::f_base);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row0 = warp * 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row0 = warp * 16;
+  const int xb = lane & 1, srow = row0 + (lane >> 1);
   const nsv_inr_config& cfg = a.cfg;
   const __half* wd = a.mlp + a.off_density;
   stage_weights(sh + L::wd0, L::ldx, wd, W, kIn);
@@ -723,7 +779,7 @@ __global__ void __launch_bounds__(kTile, 1) inr_render_kernel(const __grid_const
   const int64_t n_tiles = (total + kTile - 1) / kTile;
   const float invS = 1.f / (float)a.S;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t sidx = tile * kTile + tid;
+    const int64_t sidx = tile * kTile + srow;
     const bool valid = sidx < total;
     const int64_t p = valid ? sidx / a.S : 0;
     float xn[3] = {0.f, 0.f, 0.f};
@@ -752,29 +808,29 @@ __global__ void __launch_bounds__(kTile, 1) inr_render_kernel(const __grid_const
     }
     encode_warp(xn, lt, cfg.grid.n_levels, a.table, sh + L::sx + (size_t)row0 * L::ldx, L::ldx);
     __syncwarp();
-    uint32_t ain[2][kIn / 16][4];
+    uint32_t ain[1][kIn / 16][4];
     load_a_frags<kIn / 16>(ain, sh + L::sx, L::ldx, row0);
-    float c[2][W / 8][4];
+    float c[1][W / 8][4];
     warp_gemm_fwd<kIn / 16, W / 8>(c, ain, sh + L::wd0, L::ldx);
-    uint32_t ah[2][W / 16][4];
+    uint32_t ah[1][W / 16][4];
     acc_to_a<W / 8, true>(ah, c);
 #pragma unroll
     for (int l = 1; l < DEPTH; ++l) {
       warp_gemm_fwd<W / 16, W / 8>(c, ah, sh + L::wdh + (size_t)(l - 1) * W * L::ldh, L::ldh);
       acc_to_a<W / 8, true>(ah, c);
     }
-    float co[2][2][4];
+    float co[1][2][4];
     warp_gemm_fwd<W / 16, 2>(co, ah, sh + L::wdo, L::ldh);
     store_col0(co, sf + L::fz0, row0);
     __syncwarp();
-    float rho = valid ? softplus_f(sf[L::fz0 + tid]) * invS : 0.f;
+    float rho = (valid && xb == 0) ? softplus_f(sf[L::fz0 + srow]) * invS : 0.f;
     // warp-aggregate when the whole warp renders one point
     const int64_t p0 = __shfl_sync(0xffffffffu, p, 0), p31 = __shfl_sync(0xffffffffu, p, 31);
     const bool all_valid = __all_sync(0xffffffffu, valid);
     if (all_valid && p0 == p31) {
       rho = warp_sum(rho);
       if (lane == 0) red_add(a.out + p, rho);
-    } else if (valid) {
+    } else if (valid && xb == 0) {
       red_add(a.out + p, rho);
     }
     __syncwarp();
@@ -825,25 +881,32 @@ int set_dyn_smem(K kernel, size_t bytes, const char* name) {
   return NSV_OK;
 }
 
-template <int W, int DEPTH, bool SIGMA>
-int launch_train(const FusedArgs& a, cudaStream_t st) {
-  using L = Layout<W, DEPTH, SIGMA>;
-  if (int e = set_dyn_smem(inr_train_kernel<W, DEPTH, SIGMA>, L::bytes, "nsv_inr_train_step")) return e;
-  const int64_t tiles = a.B * (int64_t)a.S / kTile;
-  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  inr_train_kernel<W, DEPTH, SIGMA><<<grid, kTile, L::bytes, st>>>(a);
+template <int W, int DEPTH, bool SIGMA, int GR>
+int launch_train_gr(const FusedArgs& a, cudaStream_t st) {
+  using L = Layout<W, DEPTH, SIGMA, GR>;
+  if (int e = set_dyn_smem(inr_train_kernel<W, DEPTH, SIGMA, GR>, L::bytes, "nsv_inr_train_step")) return e;
+  const int64_t ctas = (a.B * (int64_t)a.S / GR + L::NG - 1) / L::NG;
+  const int grid = (int)(ctas < num_sms() ? ctas : num_sms());
+  inr_train_kernel<W, DEPTH, SIGMA, GR><<<grid, kThreads, L::bytes, st>>>(a);
   if (int e = check_launch("nsv_inr_train_step")) return e;
   inr_finalize_kernel<<<1, 256, 0, st>>>(a.logit_coef, a.g_c, a.losses, a.n_slices, a.cfg.slice_scale, a.cfg.image_reg, a.cfg.delta);
   return check_launch("nsv_inr_train_step(finalize)");
 }
 
+// pixels of up to 128 samples: two independent 128-row groups per CTA; 256 samples: one 256-row group
+template <int W, int DEPTH, bool SIGMA>
+int launch_train(const FusedArgs& a, cudaStream_t st) {
+  if (a.S <= 128) return launch_train_gr<W, DEPTH, SIGMA, 128>(a, st);
+  return launch_train_gr<W, DEPTH, SIGMA, 256>(a, st);
+}
+
 template <int W, int DEPTH>
 int launch_render(const RenderArgs& a, cudaStream_t st) {
-  using L = Layout<W, DEPTH, false>;
+  using L = RenderLayout<W, DEPTH>;
   if (int e = set_dyn_smem(inr_render_kernel<W, DEPTH>, L::bytes, "nsv_inr_render")) return e;
   const int64_t tiles = (a.M * (int64_t)a.S + kTile - 1) / kTile;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  inr_render_kernel<W, DEPTH><<<grid, kTile, L::bytes, st>>>(a);
+  inr_render_kernel<W, DEPTH><<<grid, kThreads, L::bytes, st>>>(a);
   return check_launch("nsv_inr_render");
 }
 
@@ -875,8 +938,8 @@ extern "C" int nsv_inr_train_step(const nsv_inr_config* cfg, const nsv_inr_param
   NSV_REQUIRE(B > 0, "nsv_inr_train_step: B must be positive");
   int log2S = 0;
   while ((1 << log2S) < S) ++log2S;
-  if (!(S >= 32 && S <= kTile && (1 << log2S) == S) || (B * (int64_t)S) % kTile != 0) {
-    set_error("nsv_inr_train_step: fused path needs n_samples in {32,64,128,256} and B*S %% 256 == 0 (got B=%lld S=%d)", (long long)B, S);
+  if (!(S >= 32 && S <= kTile && (1 << log2S) == S) || (B * (int64_t)S) % (S <= 128 ? 128 : kTile) != 0) {
+    set_error("nsv_inr_train_step: fused path needs n_samples in {32,64,128,256} and B*S a multiple of the 128/256-sample tile (got B=%lld S=%d)", (long long)B, S);
     return NSV_EUNSUPPORTED;
   }
   if (cfg->n_levels_bias != 0) {

@@ -50,23 +50,23 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_half2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
 
 // ---- A fragments of the warp's 32 rows from a [rows][ld] fp16 shared tile (cols k0..k0+15) ----
-template <int KT>
-__device__ __forceinline__ void load_a_frags(uint32_t (&a)[2][KT][4], const __half* tile, int ld, int row0) {
+template <int KT, int MTL>
+__device__ __forceinline__ void load_a_frags(uint32_t (&a)[MTL][KT][4], const __half* tile, int ld, int row0) {
   const int lane = threadIdx.x & 31, mi = lane >> 3, r = lane & 7;
 #pragma unroll
-  for (int m = 0; m < 2; ++m)
+  for (int m = 0; m < MTL; ++m)
 #pragma unroll
     for (int kt = 0; kt < KT; ++kt)
       ldsm_x4(a[m][kt], tile + (size_t)(row0 + m * 16 + r + ((mi & 1) ? 8 : 0)) * ld + kt * 16 + ((mi >> 1) ? 8 : 0));
 }
 
 // ---- C[32 x 8*NT] = A * W^T, W row-major [8*NT][16*KT (+pad)] in shared memory ----
-template <int KT, int NT>
-__device__ __forceinline__ void warp_gemm_fwd(float (&c)[2][NT][4], const uint32_t (&a)[2][KT][4], const __half* w, int ldw) {
+template <int KT, int NT, int MTL>
+__device__ __forceinline__ void warp_gemm_fwd(float (&c)[MTL][NT][4], const uint32_t (&a)[MTL][KT][4], const __half* w, int ldw) {
   static_assert(NT % 2 == 0, "n-tiles come in pairs");
   const int lane = threadIdx.x & 31, mi = lane >> 3, r = lane & 7;
 #pragma unroll
-  for (int m = 0; m < 2; ++m)
+  for (int m = 0; m < MTL; ++m)
 #pragma unroll
     for (int n = 0; n < NT; ++n)
 #pragma unroll
@@ -78,7 +78,7 @@ __device__ __forceinline__ void warp_gemm_fwd(float (&c)[2][NT][4], const uint32
       uint32_t b[4];
       ldsm_x4(b, w + (size_t)(np * 16 + r + ((mi >> 1) ? 8 : 0)) * ldw + kt * 16 + ((mi & 1) ? 8 : 0));
 #pragma unroll
-      for (int m = 0; m < 2; ++m) {
+      for (int m = 0; m < MTL; ++m) {
         mma16816(c[m][2 * np], a[m][kt], b[0], b[1]);
         mma16816(c[m][2 * np + 1], a[m][kt], b[2], b[3]);
       }
@@ -86,12 +86,12 @@ __device__ __forceinline__ void warp_gemm_fwd(float (&c)[2][NT][4], const uint32
 }
 
 // ---- dA[32 x 8*NT] = dC[32 x 16*KT] * W, W row-major [16*KT][8*NT (+pad)] ----
-template <int KT, int NT>
-__device__ __forceinline__ void warp_gemm_dgrad(float (&c)[2][NT][4], const uint32_t (&a)[2][KT][4], const __half* w, int ldw) {
+template <int KT, int NT, int MTL>
+__device__ __forceinline__ void warp_gemm_dgrad(float (&c)[MTL][NT][4], const uint32_t (&a)[MTL][KT][4], const __half* w, int ldw) {
   static_assert(NT % 2 == 0, "n-tiles come in pairs");
   const int lane = threadIdx.x & 31, mi = lane >> 3, r = lane & 7;
 #pragma unroll
-  for (int m = 0; m < 2; ++m)
+  for (int m = 0; m < MTL; ++m)
 #pragma unroll
     for (int n = 0; n < NT; ++n)
 #pragma unroll
@@ -103,7 +103,7 @@ __device__ __forceinline__ void warp_gemm_dgrad(float (&c)[2][NT][4], const uint
       uint32_t b[4];
       ldsm_x4_t(b, w + (size_t)(kt * 16 + r + ((mi & 1) ? 8 : 0)) * ldw + np * 16 + ((mi >> 1) ? 8 : 0));
 #pragma unroll
-      for (int m = 0; m < 2; ++m) {
+      for (int m = 0; m < MTL; ++m) {
         mma16816(c[m][2 * np], a[m][kt], b[0], b[1]);
         mma16816(c[m][2 * np + 1], a[m][kt], b[2], b[3]);
       }
@@ -111,10 +111,10 @@ __device__ __forceinline__ void warp_gemm_dgrad(float (&c)[2][NT][4], const uint
 }
 
 // ---- accumulator fragment -> next layer's A fragment (optionally ReLU), all in registers ----
-template <int NT, bool kRelu>
-__device__ __forceinline__ void acc_to_a(uint32_t (&a)[2][NT / 2][4], const float (&c)[2][NT][4]) {
+template <int NT, bool kRelu, int MTL>
+__device__ __forceinline__ void acc_to_a(uint32_t (&a)[MTL][NT / 2][4], const float (&c)[MTL][NT][4]) {
 #pragma unroll
-  for (int m = 0; m < 2; ++m)
+  for (int m = 0; m < MTL; ++m)
 #pragma unroll
     for (int kt = 0; kt < NT / 2; ++kt)
 #pragma unroll
@@ -128,12 +128,37 @@ __device__ __forceinline__ void acc_to_a(uint32_t (&a)[2][NT / 2][4], const floa
       }
 }
 
+// ---- ReLU bookkeeping in registers: bit (m*NT + n)*4 + k set <=> accumulator element > 0 ----
+template <int NT, int MTL>
+__device__ __forceinline__ uint64_t relu_bits(const float (&c)[MTL][NT][4]) {
+  static_assert(MTL * NT * 4 <= 64, "mask must fit 64 bits");
+  uint64_t bits = 0;
+#pragma unroll
+  for (int m = 0; m < MTL; ++m)
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (c[m][n][k] > 0.f) bits |= 1ull << ((m * NT + n) * 4 + k);
+  return bits;
+}
+template <int NT, int MTL>
+__device__ __forceinline__ void apply_relu_bits(float (&c)[MTL][NT][4], uint64_t bits) {
+#pragma unroll
+  for (int m = 0; m < MTL; ++m)
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (!((bits >> ((m * NT + n) * 4 + k)) & 1ull)) c[m][n][k] = 0.f;
+}
+
 // ---- park an A-fragment set (fp16) into a [rows][ld] shared tile, cols 0..16*KT-1 ----
-template <int KT>
-__device__ __forceinline__ void store_a_frags(const uint32_t (&a)[2][KT][4], __half* tile, int ld, int row0) {
+template <int KT, int MTL>
+__device__ __forceinline__ void store_a_frags(const uint32_t (&a)[MTL][KT][4], __half* tile, int ld, int row0) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
-  for (int m = 0; m < 2; ++m)
+  for (int m = 0; m < MTL; ++m)
 #pragma unroll
     for (int kt = 0; kt < KT; ++kt) {
       __half* p = tile + (size_t)(row0 + m * 16 + g) * ld + kt * 16 + 2 * t;
@@ -145,11 +170,11 @@ __device__ __forceinline__ void store_a_frags(const uint32_t (&a)[2][KT][4], __h
 }
 
 // ---- ReLU backward on fragments: zero dA where the parked activation (fp16, same layout) is <= 0 ----
-template <int NT>
-__device__ __forceinline__ void relu_mask_acc(float (&c)[2][NT][4], const __half* act_tile, int ld, int row0) {
+template <int NT, int MTL>
+__device__ __forceinline__ void relu_mask_acc(float (&c)[MTL][NT][4], const __half* act_tile, int ld, int row0) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
-  for (int m = 0; m < 2; ++m)
+  for (int m = 0; m < MTL; ++m)
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
       const __half* p = act_tile + (size_t)(row0 + m * 16 + g) * ld + n * 8 + 2 * t;
@@ -176,9 +201,10 @@ struct WgradSplit {
 
 template <int OUT, int IN, int NW>
 __device__ __forceinline__ void warp_wgrad(float (&acc)[WgradSplit<OUT, IN, NW>::NTW][4], const __half* dc_tile, int ld_dc,
-                                           const __half* a_tile, int ld_a, int rows) {
+                                           const __half* a_tile, int ld_a, int rows, int warp = -1) {
   using S = WgradSplit<OUT, IN, NW>;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, mi = lane >> 3, r = lane & 7;
+  if (warp < 0) warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, mi = lane >> 3, r = lane & 7;
   const int mt = warp % S::MT, part = warp / S::MT;
   if (part >= S::PARTS) return;
   const int nt0 = part * S::NTW;
