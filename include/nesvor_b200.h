@@ -215,6 +215,10 @@ int nsv_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
                    int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                    float grad_unscale, int zero_grad /* clear grad for the next iteration */, void* stream);
 
+/* tcgen05 / TMEM bring-up check used by tests/test_gpu_umma.py: runs every tensor-core operand
+ * configuration kernel A uses on fixed 128x64 / 64x64 / 128x16 fp16 inputs (no reference counterpart). */
+int nsv_umma_selftest(const void* A_f16, const void* W_f16, const void* G_f16, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,7 @@ SOURCES = {
     "mlp.cu": [],
     "inr_fused.cu": [],
     "adamw.cu": [],
+    "umma_selftest.cu": [],
 }
 
 
