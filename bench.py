@@ -159,6 +159,9 @@ def run_ours(a):
 
     nsv_build.build()
     import nesvor_b200 as nb
+    from nesvor_b200 import _lib as nsv_lib
+
+    nsv_lib.set_fused_impl(a.fused_impl)
     from nesvor_b200.data.phantom import simulate_slices
     from nesvor_b200.nesvor.fused import FusedTrainer
     from nesvor_b200.nesvor.train import Dataset
@@ -255,7 +258,7 @@ def run_ours(a):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "inr_train_kernel<64,3,false> (+1-block finalize)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": ("inr_train_kernel<64,3,false,128> (mma.sync)" if a.fused_impl == "mma" else "inr_train_tc_kernel<3,false> (tcgen05/TMEM)") + " + 1-block finalize", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                 "kernel_queries_per_s": n_q / (k_ms * 1e-3)}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
@@ -285,6 +288,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--fused-impl", default="auto", choices=["auto", "mma", "tcgen05"], help="implementation of kernel A")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference_arm(a)

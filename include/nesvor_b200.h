@@ -195,6 +195,10 @@ typedef struct nsv_inr_grads {    /* device pointers, all fp32, caller zero-fill
 /* number of fp16 elements of the packed MLP buffer and per-net offsets (host helper) */
 int64_t nsv_inr_mlp_layout(const nsv_inr_config* h_cfg, int64_t* h_offsets /* [3]: density, sigma, bias */);
 
+/* which implementation of kernel A nsv_inr_train_step uses: 0 = auto (tcgen05/TMEM when instantiated for the
+ * configuration, else mma.sync), 1 = mma.sync fragments, 2 = tcgen05/TMEM only (NSV_EUNSUPPORTED otherwise) */
+int nsv_set_fused_impl(int impl);
+
 int nsv_inr_train_step(const nsv_inr_config* h_cfg, const nsv_inr_params* h_params, const nsv_inr_grads* h_grads,
                        const float* xyz /* [B,3] */, const float* v /* [B] */, const int64_t* slice_idx /* [B] */,
                        const float* noise /* [B,S,3] or NULL -> in-kernel Philox(seed, offset) */,

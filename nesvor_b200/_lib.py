@@ -138,3 +138,12 @@ def make_grid_meta(n_levels: int, n_features: int, log2_hashmap_size: int, base_
     if total < 0:
         check(int(total), "nsv_grid_meta_init")
     return m, int(total)
+
+
+FUSED_IMPLS = {"auto": 0, "mma": 1, "tcgen05": 2}
+
+
+def set_fused_impl(name: str) -> None:
+    """Selects the implementation of kernel A: "auto" (tcgen05/TMEM when instantiated, else mma.sync),
+    "mma" (mma.sync fragments) or "tcgen05" (fail with FusedUnsupported if not instantiated)."""
+    check(lib().nsv_set_fused_impl(ctypes.c_int(FUSED_IMPLS[name])), "nsv_set_fused_impl")

@@ -27,6 +27,7 @@ SOURCES = {
     "hashgrid.cu": [],
     "mlp.cu": [],
     "inr_fused.cu": [],
+    "inr_fused_tc.cu": [],
     "adamw.cu": [],
     "umma_selftest.cu": [],
 }

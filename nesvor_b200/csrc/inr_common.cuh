@@ -1,0 +1,261 @@
+// inr_common.cuh -- device code shared by the two implementations of kernel A (inr_fused.cu: mma.sync
+// fragments; inr_fused_tc.cu: tcgen05 / TMEM): argument block, level table, Philox noise, the paired-lane
+// hash-grid gather / scatter, loss helpers and the 1-block finalize kernel.
+#pragma once
+#include "hashgrid.cuh"
+#include "pose.cuh"
+
+namespace nsv {
+namespace fused {
+
+constexpr int kTile = 256;     // sample rows per CTA
+constexpr int kThreads = 512;  // 16 warps; a warp owns 16 rows, lane = (row = lane >> 1, x-corner = lane & 1)
+constexpr int kIn = 32, kOutP = 16;
+constexpr int kLddx = kIn + 1;
+
+// ---- level metadata staged in shared memory (dynamic indexing of kernel params costs an LDC miss) ----
+struct LevelTable {
+  float scale[kIn / 2];
+  uint32_t res[kIn / 2], size[kIn / 2], offset[kIn / 2], hashed[kIn / 2];
+};
+struct FusedArgs {
+  nsv_inr_config cfg;
+  const __half* table;
+  const __half* mlp;
+  const float* axisangle;
+  const float* psf_sigma;
+  const float* slice_embedding;
+  const float* logit_coef;
+  const float* log_var_slice;
+  int n_slices;
+  float* g_table;
+  float* g_mlp;
+  float* g_axisangle;
+  float* g_se;
+  float* g_c;
+  float* g_lvs;
+  float* losses;
+  const float* xyz;
+  const float* v;
+  const int64_t* slice_idx;
+  const float* noise;
+  uint64_t seed, offset;
+  float* v_out;
+  int64_t B;
+  int S, log2S;
+  int64_t off_density, off_sigma;
+};
+
+// ---- Philox4x32-10 + Box-Muller: three N(0,1) per (seed, sample index) ----
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ void normal3(uint64_t seed, uint64_t idx, float e[3]) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float u0 = ((float)r.x + 0.5f) * 2.3283064365386963e-10f, u1 = ((float)r.y + 0.5f) * 2.3283064365386963e-10f;
+  const float u2 = ((float)r.z + 0.5f) * 2.3283064365386963e-10f, u3 = ((float)r.w + 0.5f) * 2.3283064365386963e-10f;
+  const float r0 = sqrtf(-2.f * __logf(u0)), r1 = sqrtf(-2.f * __logf(u2));
+  float s, c;
+  __sincosf(6.283185307179586f * u1, &s, &c);
+  e[0] = r0 * c;
+  e[1] = r0 * s;
+  e[2] = r1 * __cosf(6.283185307179586f * u3);
+}
+
+__device__ __forceinline__ LevelGeom level_from(const LevelTable& t, int l) {
+  LevelGeom g;
+  g.scale = t.scale[l];
+  g.res = t.res[l];
+  g.size = t.size[l];
+  g.offset = t.offset[l];
+  g.hashed = t.hashed[l];
+  return g;
+}
+// The 4 (y,z) corner entries of one lane (x-corner fixed): e[q], q = yb + 2 zb, level offset included.
+// The hashed / dense decision is warp-uniform and made once per level; corners are derived
+// incrementally (hash: two multiplies + XORs; dense: one base index + strides).
+__device__ __forceinline__ void corner_entries(const LevelGeom& lv, uint32_t cx, uint32_t gy, uint32_t gz, uint32_t e[4]) {
+  if (lv.hashed) {
+    const uint32_t hy0 = gy * 2654435761u, hy1 = hy0 + 2654435761u;
+    const uint32_t hz0 = gz * 805459861u, hz1 = hz0 + 805459861u;
+    e[0] = cx ^ hy0 ^ hz0;
+    e[1] = cx ^ hy1 ^ hz0;
+    e[2] = cx ^ hy0 ^ hz1;
+    e[3] = cx ^ hy1 ^ hz1;
+    if ((lv.size & (lv.size - 1)) == 0) {
+      const uint32_t mask = lv.size - 1;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) e[q] = (e[q] & mask) + lv.offset;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) e[q] = e[q] % lv.size + lv.offset;
+    }
+  } else {
+    const uint32_t sy = lv.res, sz = lv.res * lv.res;
+    e[0] = cx + gy * sy + gz * sz;
+    e[1] = e[0] + sy;
+    e[2] = e[0] + sz;
+    e[3] = e[2] + sy;
+    if (e[3] >= lv.size || e[0] > e[3]) {  // wrap-around only for out-of-box samples (tcnn semantics: mod T_l)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) e[q] %= lv.size;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) e[q] += lv.offset;
+  }
+}
+
+// Lane mapping of the whole kernel: a warp owns 16 samples, lane = (sample s = lane >> 1, x-corner
+// xb = lane & 1); both lanes of a pair carry the sample's geometry.  The two x-neighbours of a grid
+// cell are adjacent table entries (dense levels always, hashed levels whenever g_x is even), so the
+// two lanes of a pair hit the same 128-byte line and a warp-wide LDG / RED touches <= 16 lines
+// instead of 32 -- the L1 wavefront count, which bounds the gather / scatter phases, halves.  Each
+// lane blends / scatters its 4 (y,z) corners; one shfl_xor(1) combines the pair.
+
+// ---- phase 0: encode the warp's 16 samples into their fp16 rows of the shared tile ----
+// `store(l, half2)` parks features (2l, 2l+1) of this lane's sample; called by the xb == 0 lane for l < n_levels
+// and by both lanes (interleaved) for the zero padding up to kIn/2
+template <typename StoreFn>
+__device__ __forceinline__ void encode_warp(const float xn[3], const LevelTable& lt, int n_levels, const __half* __restrict__ table,
+                                            StoreFn store) {
+  const int lane = threadIdx.x & 31, xb = lane & 1;
+#pragma unroll 4
+  for (int l = 0; l < n_levels; ++l) {
+    const LevelGeom lv = level_from(lt, l);
+    uint32_t g[3], e[4];
+    float w[3];
+    level_pos(xn, lv.scale, g, w);
+    corner_entries(lv, g[0] + xb, g[1], g[2], e);
+    float2 f[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f[q] = load_pair(table, e[q]);
+    const float wx = xb ? w[0] : 1.f - w[0];
+    const float wy0 = wx * (1.f - w[1]), wy1 = wx * w[1];
+    const float wq[4] = {wy0 * (1.f - w[2]), wy1 * (1.f - w[2]), wy0 * w[2], wy1 * w[2]};
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      a0 = fmaf(wq[q], f[q].x, a0);
+      a1 = fmaf(wq[q], f[q].y, a1);
+    }
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+    if (xb == 0) store(l, __floats2half2_rn(a0, a1));
+  }
+  // zero the padding columns (the pair splits them)
+  for (int l = n_levels + xb; l < kIn / 2; l += 2) store(l, __floats2half2_rn(0.f, 0.f));
+}
+
+// ---- phase 3 tail: scatter dL/d(features) of the warp's 16 samples; optionally dL/dx through the grid ----
+// gx: dL/dx_normalised of this lane's sample (both lanes of a pair)
+// `fetch(l)` returns dL/d(features 2l, 2l+1) of this lane's sample (both lanes of a pair call it)
+template <bool kInputGrad, typename FetchFn>
+__device__ __forceinline__ void scatter_warp(const float xn[3], const LevelTable& lt, int n_levels, const __half* __restrict__ table,
+                                             FetchFn fetch, float inv_scale, float* __restrict__ g_table, float gx[3]) {
+  const int lane = threadIdx.x & 31, xb = lane & 1;
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int l = 0; l < n_levels; ++l) {
+    const LevelGeom lv = level_from(lt, l);
+    const float2 gq = fetch(l);
+    const float g0 = gq.x * inv_scale, g1 = gq.y * inv_scale;
+    uint32_t g[3], e[4];
+    float w[3];
+    level_pos(xn, lv.scale, g, w);
+    corner_entries(lv, g[0] + xb, g[1], g[2], e);
+    const float wx = xb ? w[0] : 1.f - w[0];
+    if (kInputGrad) {
+      float2 f[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) f[q] = load_pair(table, e[q]);
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float dot = fmaf(f[q].x, g0, f[q].y * g1);
+        const float fy = (q & 1) ? w[1] : 1.f - w[1], fz = (q >> 1) ? w[2] : 1.f - w[2];
+        d0 += (xb ? dot : -dot) * fy * fz;
+        d1 += ((q & 1) ? dot : -dot) * wx * fz;
+        d2 += ((q >> 1) ? dot : -dot) * wx * fy;
+      }
+      acc[0] = fmaf(lv.scale, d0, acc[0]);
+      acc[1] = fmaf(lv.scale, d1, acc[1]);
+      acc[2] = fmaf(lv.scale, d2, acc[2]);
+    }
+    if (g0 != 0.f || g1 != 0.f) {
+      const float wy0 = wx * (1.f - w[1]), wy1 = wx * w[1];
+      const float wt[4] = {wy0 * (1.f - w[2]), wy1 * (1.f - w[2]), wy0 * w[2], wy1 * w[2]};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) red_add_v2(g_table + 2 * (size_t)e[q], wt[q] * g0, wt[q] * g1);
+    }
+  }
+  if (kInputGrad) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) gx[d] = acc[d] + __shfl_xor_sync(0xffffffffu, acc[d], 1);
+  }
+}
+
+__device__ __forceinline__ float softplus_f(float z) { return z > 20.f ? z : log1pf(expf(z)); }
+__device__ __forceinline__ float sigmoid_f(float z) { return 1.f / (1.f + expf(-z)); }
+
+__device__ __forceinline__ void group_barrier(int grp, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void red_shared(float* p, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "f"(v) : "memory");
+}
+
+// softmax chain rule for the slice scale + final loss values (1 block)
+static __global__ void __launch_bounds__(256) inr_finalize_kernel(const float* __restrict__ logit_coef, float* __restrict__ g_c,
+                                                           float* __restrict__ losses, int n_slices, int slice_scale, int image_reg,
+                                                           float delta) {
+  __shared__ float red[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (slice_scale) {
+    float mx = -INFINITY;
+    for (int k = tid; k < n_slices; k += 256) mx = fmaxf(mx, logit_coef[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int k = 1; k < 8; ++k) mx = fmaxf(mx, red[k]);
+    __syncthreads();
+    float se = 0.f;
+    for (int k = tid; k < n_slices; k += 256) se += expf(logit_coef[k] - mx);
+    se = warp_sum(se);
+    if (lane == 0) red[warp] = se;
+    __syncthreads();
+    se = 0.f;
+    for (int k = 0; k < 8; ++k) se += red[k];
+    __syncthreads();
+    const float lse = mx + logf(se);
+    float dot = 0.f;  // sum_k gc_k c_k
+    for (int k = tid; k < n_slices; k += 256) dot += g_c[k] * (float)n_slices * expf(logit_coef[k] - lse);
+    dot = warp_sum(dot);
+    if (lane == 0) red[warp] = dot;
+    __syncthreads();
+    dot = 0.f;
+    for (int k = 0; k < 8; ++k) dot += red[k];
+    for (int k = tid; k < n_slices; k += 256) {
+      const float c = (float)n_slices * expf(logit_coef[k] - lse);
+      g_c[k] = c * (g_c[k] - dot / (float)n_slices);  // in place: dL/dlogit_k
+    }
+  }
+  if (tid == 0 && image_reg == 2) losses[3] = delta * (losses[3] - 1.f);
+}
+
+
+// implemented in inr_fused_tc.cu; returns NSV_EUNSUPPORTED when the configuration has no tcgen05 instantiation
+int launch_train_tc(const FusedArgs& a, cudaStream_t st);
+
+}  // namespace fused
+}  // namespace nsv

@@ -21,50 +21,12 @@
 //     gradient with vector reductions (red.global.add.v2.f32), and -- when poses are optimised --
 //     dL/dx through the grid, reduced per pixel and pushed through the Rodrigues VJP.
 // Nothing but the table gradient, O(weights) and O(slices) values is written to global memory.
-#include "hashgrid.cuh"
+#include "inr_common.cuh"
 #include "mlp_mma.cuh"
-#include "pose.cuh"
 
 namespace nsv {
+namespace fused {
 namespace {
-
-constexpr int kTile = 256;     // sample rows per CTA
-constexpr int kThreads = 512;  // 16 warps; a warp owns 16 rows, lane = (row = lane >> 1, x-corner = lane & 1)
-constexpr int kIn = 32, kOutP = 16;
-constexpr int kLddx = kIn + 1;
-
-// ---- level metadata staged in shared memory (dynamic indexing of kernel params costs an LDC miss) ----
-struct LevelTable {
-  float scale[kIn / 2];
-  uint32_t res[kIn / 2], size[kIn / 2], offset[kIn / 2], hashed[kIn / 2];
-};
-struct FusedArgs {
-  nsv_inr_config cfg;
-  const __half* table;
-  const __half* mlp;
-  const float* axisangle;
-  const float* psf_sigma;
-  const float* slice_embedding;
-  const float* logit_coef;
-  const float* log_var_slice;
-  int n_slices;
-  float* g_table;
-  float* g_mlp;
-  float* g_axisangle;
-  float* g_se;
-  float* g_c;
-  float* g_lvs;
-  float* losses;
-  const float* xyz;
-  const float* v;
-  const int64_t* slice_idx;
-  const float* noise;
-  uint64_t seed, offset;
-  float* v_out;
-  int64_t B;
-  int S, log2S;
-  int64_t off_density, off_sigma;
-};
 
 // Shared-memory plan.  A CTA hosts NG = 256/GR independent groups of GR rows (GR/32 warps); each
 // group owns its activation tiles, the CTA shares weights, level table and the fp32 weight-gradient
@@ -124,162 +86,6 @@ struct RenderLayout {
   static constexpr size_t bytes = f_base + (flt + (sizeof(LevelTable) + 3) / 4) * 4;
 };
 
-// ---- Philox4x32-10 + Box-Muller: three N(0,1) per (seed, sample index) ----
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += 0x9E3779B9u;
-    k.y += 0xBB67AE85u;
-  }
-  return c;
-}
-__device__ __forceinline__ void normal3(uint64_t seed, uint64_t idx, float e[3]) {
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  const float u0 = ((float)r.x + 0.5f) * 2.3283064365386963e-10f, u1 = ((float)r.y + 0.5f) * 2.3283064365386963e-10f;
-  const float u2 = ((float)r.z + 0.5f) * 2.3283064365386963e-10f, u3 = ((float)r.w + 0.5f) * 2.3283064365386963e-10f;
-  const float r0 = sqrtf(-2.f * __logf(u0)), r1 = sqrtf(-2.f * __logf(u2));
-  float s, c;
-  __sincosf(6.283185307179586f * u1, &s, &c);
-  e[0] = r0 * c;
-  e[1] = r0 * s;
-  e[2] = r1 * __cosf(6.283185307179586f * u3);
-}
-
-__device__ __forceinline__ LevelGeom level_from(const LevelTable& t, int l) {
-  LevelGeom g;
-  g.scale = t.scale[l];
-  g.res = t.res[l];
-  g.size = t.size[l];
-  g.offset = t.offset[l];
-  g.hashed = t.hashed[l];
-  return g;
-}
-// The 4 (y,z) corner entries of one lane (x-corner fixed): e[q], q = yb + 2 zb, level offset included.
-// The hashed / dense decision is warp-uniform and made once per level; corners are derived
-// incrementally (hash: two multiplies + XORs; dense: one base index + strides).
-__device__ __forceinline__ void corner_entries(const LevelGeom& lv, uint32_t cx, uint32_t gy, uint32_t gz, uint32_t e[4]) {
-  if (lv.hashed) {
-    const uint32_t hy0 = gy * 2654435761u, hy1 = hy0 + 2654435761u;
-    const uint32_t hz0 = gz * 805459861u, hz1 = hz0 + 805459861u;
-    e[0] = cx ^ hy0 ^ hz0;
-    e[1] = cx ^ hy1 ^ hz0;
-    e[2] = cx ^ hy0 ^ hz1;
-    e[3] = cx ^ hy1 ^ hz1;
-    if ((lv.size & (lv.size - 1)) == 0) {
-      const uint32_t mask = lv.size - 1;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) e[q] = (e[q] & mask) + lv.offset;
-    } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) e[q] = e[q] % lv.size + lv.offset;
-    }
-  } else {
-    const uint32_t sy = lv.res, sz = lv.res * lv.res;
-    e[0] = cx + gy * sy + gz * sz;
-    e[1] = e[0] + sy;
-    e[2] = e[0] + sz;
-    e[3] = e[2] + sy;
-    if (e[3] >= lv.size || e[0] > e[3]) {  // wrap-around only for out-of-box samples (tcnn semantics: mod T_l)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) e[q] %= lv.size;
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) e[q] += lv.offset;
-  }
-}
-
-// Lane mapping of the whole kernel: a warp owns 16 samples, lane = (sample s = lane >> 1, x-corner
-// xb = lane & 1); both lanes of a pair carry the sample's geometry.  The two x-neighbours of a grid
-// cell are adjacent table entries (dense levels always, hashed levels whenever g_x is even), so the
-// two lanes of a pair hit the same 128-byte line and a warp-wide LDG / RED touches <= 16 lines
-// instead of 32 -- the L1 wavefront count, which bounds the gather / scatter phases, halves.  Each
-// lane blends / scatters its 4 (y,z) corners; one shfl_xor(1) combines the pair.
-
-// ---- phase 0: encode the warp's 16 samples into their fp16 rows of the shared tile ----
-__device__ __forceinline__ void encode_warp(const float xn[3], const LevelTable& lt, int n_levels, const __half* __restrict__ table,
-                                            __half* rows /* first row of this warp */, int ld) {
-  const int lane = threadIdx.x & 31, xb = lane & 1, sl = lane >> 1;
-  __half* row = rows + (size_t)sl * ld;
-#pragma unroll 4
-  for (int l = 0; l < n_levels; ++l) {
-    const LevelGeom lv = level_from(lt, l);
-    uint32_t g[3], e[4];
-    float w[3];
-    level_pos(xn, lv.scale, g, w);
-    corner_entries(lv, g[0] + xb, g[1], g[2], e);
-    float2 f[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) f[q] = load_pair(table, e[q]);
-    const float wx = xb ? w[0] : 1.f - w[0];
-    const float wy0 = wx * (1.f - w[1]), wy1 = wx * w[1];
-    const float wq[4] = {wy0 * (1.f - w[2]), wy1 * (1.f - w[2]), wy0 * w[2], wy1 * w[2]};
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      a0 = fmaf(wq[q], f[q].x, a0);
-      a1 = fmaf(wq[q], f[q].y, a1);
-    }
-    a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
-    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-    if (xb == 0) *reinterpret_cast<__half2*>(row + 2 * l) = __floats2half2_rn(a0, a1);
-  }
-  // zero the padding columns (the pair splits them)
-  for (int l = n_levels + xb; l < kIn / 2; l += 2) *reinterpret_cast<uint32_t*>(row + 2 * l) = 0u;
-}
-
-// ---- phase 3 tail: scatter dL/d(features) of the warp's 16 samples; optionally dL/dx through the grid ----
-// grows: fp32 [16][kLddx] rows of this warp; gx: dL/dx_normalised of this lane's sample (both lanes of a pair)
-template <bool kInputGrad>
-__device__ __forceinline__ void scatter_warp(const float xn[3], const LevelTable& lt, int n_levels, const __half* __restrict__ table,
-                                             const float* grows, float inv_scale, float* __restrict__ g_table, float gx[3]) {
-  const int lane = threadIdx.x & 31, xb = lane & 1, sl = lane >> 1;
-  const float* gr = grows + (size_t)sl * kLddx;
-  float acc[3] = {0.f, 0.f, 0.f};
-#pragma unroll 4
-  for (int l = 0; l < n_levels; ++l) {
-    const LevelGeom lv = level_from(lt, l);
-    const float g0 = gr[2 * l] * inv_scale, g1 = gr[2 * l + 1] * inv_scale;
-    uint32_t g[3], e[4];
-    float w[3];
-    level_pos(xn, lv.scale, g, w);
-    corner_entries(lv, g[0] + xb, g[1], g[2], e);
-    const float wx = xb ? w[0] : 1.f - w[0];
-    if (kInputGrad) {
-      float2 f[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) f[q] = load_pair(table, e[q]);
-      float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float dot = fmaf(f[q].x, g0, f[q].y * g1);
-        const float fy = (q & 1) ? w[1] : 1.f - w[1], fz = (q >> 1) ? w[2] : 1.f - w[2];
-        d0 += (xb ? dot : -dot) * fy * fz;
-        d1 += ((q & 1) ? dot : -dot) * wx * fz;
-        d2 += ((q >> 1) ? dot : -dot) * wx * fy;
-      }
-      acc[0] = fmaf(lv.scale, d0, acc[0]);
-      acc[1] = fmaf(lv.scale, d1, acc[1]);
-      acc[2] = fmaf(lv.scale, d2, acc[2]);
-    }
-    if (g0 != 0.f || g1 != 0.f) {
-      const float wy0 = wx * (1.f - w[1]), wy1 = wx * w[1];
-      const float wt[4] = {wy0 * (1.f - w[2]), wy1 * (1.f - w[2]), wy0 * w[2], wy1 * w[2]};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) red_add_v2(g_table + 2 * (size_t)e[q], wt[q] * g0, wt[q] * g1);
-    }
-  }
-  if (kInputGrad) {
-#pragma unroll
-    for (int d = 0; d < 3; ++d) gx[d] = acc[d] + __shfl_xor_sync(0xffffffffu, acc[d], 1);
-  }
-}
-
-__device__ __forceinline__ float softplus_f(float z) { return z > 20.f ? z : log1pf(expf(z)); }
-__device__ __forceinline__ float sigmoid_f(float z) { return 1.f / (1.f + expf(-z)); }
-
 // column 0 of a 2-n-tile accumulator -> per-row scalar array (rows of this warp)
 template <int MTL>
 __device__ __forceinline__ void store_col0(const float (&c)[MTL][2][4], float* dst, int row0) {
@@ -292,14 +98,6 @@ __device__ __forceinline__ void store_col0(const float (&c)[MTL][2][4], float* d
       dst[row0 + m * 16 + g + 8] = c[m][0][2];
     }
   }
-}
-
-__device__ __forceinline__ void group_barrier(int grp, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(nthreads) : "memory");
-}
-
-__device__ __forceinline__ void red_shared(float* p, float v) {
-  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_u32(p)), "f"(v) : "memory");
 }
 
 // add a warp's freshly computed dW block into the CTA's shared fp32 accumulator (row-major [OUT][IN])
@@ -412,7 +210,10 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_kernel(const __grid_con
         xn[i] = (xw[i] - cfg.bbox_lo[i]) / (cfg.bbox_hi[i] - cfg.bbox_lo[i]);
       }
     }
-    encode_warp(xn, lt, cfg.grid.n_levels, a.table, sh + L::sx + (size_t)row0 * L::ldx, L::ldx);
+    {
+      __half* xrow = sh + L::sx + (size_t)srow * L::ldx;
+      encode_warp(xn, lt, cfg.grid.n_levels, a.table, [&](int l, __half2 v) { *reinterpret_cast<__half2*>(xrow + 2 * l) = v; });
+    }
     __syncwarp();
 
     // ================= phase 1: density MLP forward (warp-local, one m16 tile per warp) =================
@@ -632,10 +433,11 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_kernel(const __grid_con
     }
     __syncwarp();
     // ---- scatter into the table gradient (+ pose gradient) ----
-    const float* grows = sdx + (size_t)row0 * kLddx;
+    const float* grow_s = sdx + (size_t)srow * kLddx;
+    auto fetch = [&](int l) { return make_float2(grow_s[2 * l], grow_s[2 * l + 1]); };
     if (cfg.pose_grad) {
       float gx[3];
-      scatter_warp<true>(xn, lt, cfg.grid.n_levels, a.table, grows, inv_gscale, a.g_table, gx);
+      scatter_warp<true>(xn, lt, cfg.grid.n_levels, a.table, fetch, inv_gscale, a.g_table, gx);
       float gwd[3], part[12];
 #pragma unroll
       for (int i = 0; i < 3; ++i) gwd[i] = xb ? 0.f : gx[i] / (cfg.bbox_hi[i] - cfg.bbox_lo[i]);  // one lane per sample contributes
@@ -670,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_kernel(const __grid_con
       }
     } else {
       float gx[3];
-      scatter_warp<false>(xn, lt, cfg.grid.n_levels, a.table, grows, inv_gscale, a.g_table, gx);
+      scatter_warp<false>(xn, lt, cfg.grid.n_levels, a.table, fetch, inv_gscale, a.g_table, gx);
     }
   }
 
@@ -693,46 +495,6 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_kernel(const __grid_con
     red_add(a.losses + 1, loss_s);
     red_add(a.losses + 3, loss_i);
   }
-}
-
-// softmax chain rule for the slice scale + final loss values (1 block)
-__global__ void __launch_bounds__(256) inr_finalize_kernel(const float* __restrict__ logit_coef, float* __restrict__ g_c,
-                                                           float* __restrict__ losses, int n_slices, int slice_scale, int image_reg,
-                                                           float delta) {
-  __shared__ float red[8];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (slice_scale) {
-    float mx = -INFINITY;
-    for (int k = tid; k < n_slices; k += 256) mx = fmaxf(mx, logit_coef[k]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) red[warp] = mx;
-    __syncthreads();
-    mx = red[0];
-    for (int k = 1; k < 8; ++k) mx = fmaxf(mx, red[k]);
-    __syncthreads();
-    float se = 0.f;
-    for (int k = tid; k < n_slices; k += 256) se += expf(logit_coef[k] - mx);
-    se = warp_sum(se);
-    if (lane == 0) red[warp] = se;
-    __syncthreads();
-    se = 0.f;
-    for (int k = 0; k < 8; ++k) se += red[k];
-    __syncthreads();
-    const float lse = mx + logf(se);
-    float dot = 0.f;  // sum_k gc_k c_k
-    for (int k = tid; k < n_slices; k += 256) dot += g_c[k] * (float)n_slices * expf(logit_coef[k] - lse);
-    dot = warp_sum(dot);
-    if (lane == 0) red[warp] = dot;
-    __syncthreads();
-    dot = 0.f;
-    for (int k = 0; k < 8; ++k) dot += red[k];
-    for (int k = tid; k < n_slices; k += 256) {
-      const float c = (float)n_slices * expf(logit_coef[k] - lse);
-      g_c[k] = c * (g_c[k] - dot / (float)n_slices);  // in place: dL/dlogit_k
-    }
-  }
-  if (tid == 0 && image_reg == 2) losses[3] = delta * (losses[3] - 1.f);
 }
 
 // ------------------------------------------------------------------------------------- renderer
@@ -806,7 +568,10 @@ __global__ void __launch_bounds__(kThreads, 1) inr_render_kernel(const __grid_co
 #pragma unroll
       for (int i = 0; i < 3; ++i) xn[i] = (xw[i] - cfg.bbox_lo[i]) / (cfg.bbox_hi[i] - cfg.bbox_lo[i]);
     }
-    encode_warp(xn, lt, cfg.grid.n_levels, a.table, sh + L::sx + (size_t)row0 * L::ldx, L::ldx);
+    {
+      __half* xrow = sh + L::sx + (size_t)srow * L::ldx;
+      encode_warp(xn, lt, cfg.grid.n_levels, a.table, [&](int l, __half2 v) { *reinterpret_cast<__half2*>(xrow + 2 * l) = v; });
+    }
     __syncwarp();
     uint32_t ain[1][kIn / 16][4];
     load_a_frags<kIn / 16>(ain, sh + L::sx, L::ldx, row0);
@@ -911,14 +676,26 @@ int launch_render(const RenderArgs& a, cudaStream_t st) {
 }
 
 }  // namespace
+}  // namespace fused
 }  // namespace nsv
+
+namespace nsv { namespace fused { static int g_fused_impl = 0; } }
+
+extern "C" int nsv_set_fused_impl(int impl) {
+  if (impl < 0 || impl > 2) {
+    nsv::set_error("nsv_set_fused_impl: 0 = auto, 1 = mma.sync, 2 = tcgen05");
+    return NSV_EINVAL;
+  }
+  nsv::fused::g_fused_impl = impl;
+  return NSV_OK;
+}
 
 extern "C" int64_t nsv_inr_mlp_layout(const nsv_inr_config* cfg, int64_t* offsets) {
   if (!cfg) {
     nsv::set_error("nsv_inr_mlp_layout: NULL config");
     return NSV_EINVAL;
   }
-  const nsv::MlpLayout l = nsv::mlp_layout(*cfg);
+  const nsv::fused::MlpLayout l = nsv::fused::mlp_layout(*cfg);
   if (offsets) {
     offsets[0] = l.off_density;
     offsets[1] = l.off_sigma;
@@ -931,6 +708,7 @@ extern "C" int nsv_inr_train_step(const nsv_inr_config* cfg, const nsv_inr_param
                                   const float* v, const int64_t* slice_idx, const float* noise, uint64_t seed, uint64_t offset,
                                   float* v_out, int64_t B, int S, void* stream) {
   using namespace nsv;
+  using namespace nsv::fused;
   if (int e = validate_common("nsv_inr_train_step", cfg)) return e;
   NSV_REQUIRE(prm && g && xyz && v && slice_idx, "nsv_inr_train_step: NULL pointer");
   NSV_REQUIRE(prm->table_f16 && prm->mlp_f16 && prm->axisangle && prm->psf_sigma && g->table && g->mlp && g->losses,
@@ -988,6 +766,10 @@ extern "C" int nsv_inr_train_step(const nsv_inr_config* cfg, const nsv_inr_param
   a.off_sigma = ml.off_sigma;
   cudaStream_t st = (cudaStream_t)stream;
   const bool sig = cfg->pixel_variance != 0;
+  if (g_fused_impl != 1) {  // tcgen05 / TMEM implementation when it is instantiated for this configuration
+    const int rc = launch_train_tc(a, st);
+    if (rc != NSV_EUNSUPPORTED || g_fused_impl == 2) return rc;
+  }
   if (cfg->width == 64) {
     if (sig) return launch_train<64, 1, true>(a, st);
     if (cfg->depth == 1) return launch_train<64, 1, false>(a, st);
@@ -1004,6 +786,7 @@ extern "C" int nsv_inr_render(const nsv_inr_config* cfg, const nsv_inr_params* p
                               int mat_per_point, const float* psf_sigma, int sigma_per_point, const float* noise, uint64_t seed,
                               uint64_t offset, float* out, int64_t M, int S, void* stream) {
   using namespace nsv;
+  using namespace nsv::fused;
   if (int e = validate_common("nsv_inr_render", cfg)) return e;
   NSV_REQUIRE(prm && prm->table_f16 && prm->mlp_f16, "nsv_inr_render: NULL parameters");
   NSV_REQUIRE(M >= 0 && S >= 1, "nsv_inr_render: bad sizes");

@@ -102,10 +102,22 @@ CONFIGS = {
 }
 
 
+@pytest.fixture
+def fused_impl(request):
+    from nesvor_b200 import _lib
+
+    _lib.set_fused_impl(request.param)
+    yield request.param
+    _lib.set_fused_impl("auto")
+
+
+@pytest.mark.parametrize("fused_impl", ["mma", "tcgen05"], indirect=True)
 @pytest.mark.parametrize("name", list(CONFIGS))
-def test_fused_train_step_parity(native_lib, name):
+def test_fused_train_step_parity(native_lib, name, fused_impl):
     from nesvor_b200.nesvor.fused import FusedState
 
+    if fused_impl == "tcgen05" and CONFIGS[name].get("width", 64) != 64:
+        pytest.skip("tcgen05 path is instantiated for width 64 (UMMA M = 64 wgrad)")
     args = make_args(**CONFIGS[name])
     n_slices = 9
     model, om = build_pair(args, n_slices)
@@ -118,7 +130,7 @@ def test_fused_train_step_parity(native_lib, name):
     losses, v_out = st.forward_backward(xyz.cuda(), v.cuda(), idx.cuda(), noise.cuda(), want_v_out=True)
     torch.cuda.synchronize()
     err = rel_l2(v_out.cpu(), aux["v_out"].detach())
-    print(f"{name}: rel-L2(v_out) = {err:.3e}")
+    print(f"{name} [{fused_impl}]: rel-L2(v_out) = {err:.3e}")
     assert err <= V_OUT_TOL
     got = st.loss_dict(losses.cpu())
     for k in ("MSE", "logVar", "imageReg"):
