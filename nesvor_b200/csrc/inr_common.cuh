@@ -11,6 +11,8 @@ namespace fused {
 constexpr int kTile = 256;     // sample rows per CTA
 constexpr int kThreads = 512;  // 16 warps; a warp owns 16 rows, lane = (row = lane >> 1, x-corner = lane & 1)
 constexpr int kIn = 32, kOutP = 16;
+constexpr uint32_t kAggMaxRes = 64;  // levels up to this resolution try warp-level gradient aggregation
+constexpr int kAggMaxCells = 4;      // ... when the warp's 16 samples occupy at most this many cells
 constexpr int kLddx = kIn + 1;
 
 // ---- level metadata staged in shared memory (dynamic indexing of kernel params costs an LDC miss) ----
@@ -189,9 +191,44 @@ __device__ __forceinline__ void scatter_warp(const float xn[3], const LevelTable
       acc[1] = fmaf(lv.scale, d1, acc[1]);
       acc[2] = fmaf(lv.scale, d2, acc[2]);
     }
-    if (g0 != 0.f || g1 != 0.f) {
-      const float wy0 = wx * (1.f - w[1]), wy1 = wx * w[1];
-      const float wt[4] = {wy0 * (1.f - w[2]), wy1 * (1.f - w[2]), wy0 * w[2], wy1 * w[2]};
+    const float wy0 = wx * (1.f - w[1]), wy1 = wx * w[1];
+    const float wt[4] = {wy0 * (1.f - w[2]), wy1 * (1.f - w[2]), wy0 * w[2], wy1 * w[2]};
+    bool done = false;
+    if (lv.res <= kAggMaxRes) {
+      // Coarse levels: the 16 samples of a warp (one pixel's PSF cloud) fall into a handful of cells, and a few
+      // thousand entries would receive millions of same-address reductions per iteration, which serialise in a
+      // few L2 slices (measured: 0.42 ms of a 1.26 ms kernel for the 3 coarsest levels).  So the warp first finds
+      // its distinct cells (match.any), butterfly-reduces every cell's 8 corner contributions across the 16 lanes
+      // that share an x-corner, and only the cell's leading lane pair issues reductions.
+      const uint32_t key = (g[0] & 0x3ffu) | ((g[1] & 0x3ffu) << 10) | ((g[2] & 0x3ffu) << 20);
+      const uint32_t peers = __match_any_sync(0xffffffffu, key);
+      const int my_leader = __ffs(peers) - 1;  // even lane: the xb == 0 lane of the first sample in this cell
+      uint32_t rem = __ballot_sync(0xffffffffu, lane == my_leader);
+      if (__popc(rem) <= kAggMaxCells) {
+        while (rem) {
+          const int ld = __ffs(rem) - 1;
+          rem &= rem - 1;
+          const bool mine = (my_leader == ld);
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            v[2 * q] = mine ? wt[q] * g0 : 0.f;
+            v[2 * q + 1] = mine ? wt[q] * g1 : 0.f;
+          }
+#pragma unroll
+          for (int off = 2; off < 32; off <<= 1)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+          if ((lane & ~1) == ld) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (v[2 * q] != 0.f || v[2 * q + 1] != 0.f) red_add_v2(g_table + 2 * (size_t)e[q], v[2 * q], v[2 * q + 1]);
+          }
+        }
+        done = true;
+      }
+    }
+    if (!done && (g0 != 0.f || g1 != 0.f)) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) red_add_v2(g_table + 2 * (size_t)e[q], wt[q] * g0, wt[q] * g1);
     }
