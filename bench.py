@@ -195,10 +195,12 @@ def run_ours(a):
     sync_all()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
+        torch.cuda.nvtx.range_push("nsv_timed")  # ncu --nvtx --nvtx-include "nsv_timed/" lists exactly these launches
         ev0.record()
         for _ in range(a.steps):
             losses = one_step(dataset.get_batch(B, dev))
         ev1.record()
+        torch.cuda.nvtx.range_pop()
         sync_all()
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms], device=dev)

@@ -11,7 +11,7 @@ namespace fused {
 constexpr int kTile = 256;     // sample rows per CTA
 constexpr int kThreads = 512;  // 16 warps; a warp owns 16 rows, lane = (row = lane >> 1, x-corner = lane & 1)
 constexpr int kIn = 32, kOutP = 16;
-constexpr uint32_t kAggMaxRes = 64;  // levels up to this resolution try warp-level gradient aggregation
+constexpr uint32_t kAggMaxSize = 8192;  // levels with at most this many entries try warp-level gradient aggregation
 constexpr int kAggMaxCells = 4;      // ... when the warp's 16 samples occupy at most this many cells
 constexpr int kLddx = kIn + 1;
 
@@ -194,7 +194,7 @@ __device__ __forceinline__ void scatter_warp(const float xn[3], const LevelTable
     const float wy0 = wx * (1.f - w[1]), wy1 = wx * w[1];
     const float wt[4] = {wy0 * (1.f - w[2]), wy1 * (1.f - w[2]), wy0 * w[2], wy1 * w[2]};
     bool done = false;
-    if (lv.res <= kAggMaxRes) {
+    if (lv.size <= kAggMaxSize) {
       // Coarse levels: the 16 samples of a warp (one pixel's PSF cloud) fall into a handful of cells, and a few
       // thousand entries would receive millions of same-address reductions per iteration, which serialise in a
       // few L2 slices (measured: 0.42 ms of a 1.26 ms kernel for the 3 coarsest levels).  So the warp first finds

@@ -300,12 +300,14 @@ class FusedTrainer:
         out = st.loss_dict(losses.clone())
         if self.pose and a.weight_transformation:
             out[T_REG] = self._trans_reg()  # identical on every rank: the all-reduce mean leaves it unchanged
-        dist.all_reduce(st.grad[: st.n_train], op=dist.ReduceOp.SUM)
+        from .distributed import allreduce_gradient
+
+        unscale = allreduce_gradient(st.grad[: st.n_train], dist, world)
         with torch.cuda.device(st.device):
             rc = _lib.lib().nsv_adamw_step(
                 _lib.ptr(st.flat), _lib.ptr(st.grad), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), _lib.ptr(st.flat16),
                 ctypes.c_int64(st.n_train), ctypes.c_float(self.lr), ctypes.c_float(0.9), ctypes.c_float(0.99), ctypes.c_float(1e-15),
-                ctypes.c_float(1e-2), ctypes.c_int(self.iteration), ctypes.c_float(1.0 / world), ctypes.c_int(1), _lib.stream(st.device))
+                ctypes.c_float(1e-2), ctypes.c_int(self.iteration), ctypes.c_float(unscale), ctypes.c_int(1), _lib.stream(st.device))
         _lib.check(rc, "nsv_adamw_step")
         return out
 
