@@ -147,3 +147,8 @@ def set_fused_impl(name: str) -> None:
     """Selects the implementation of kernel A: "auto" (tcgen05/TMEM when instantiated, else mma.sync),
     "mma" (mma.sync fragments) or "tcgen05" (fail with FusedUnsupported if not instantiated)."""
     check(lib().nsv_set_fused_impl(ctypes.c_int(FUSED_IMPLS[name])), "nsv_set_fused_impl")
+
+
+def set_fused_tuning(agg_max_entries: int = -1, fast_path: int = -1) -> None:
+    """Tuning / test hook of kernel A's gather-scatter loops (see include/nesvor_b200.h)."""
+    check(lib().nsv_set_fused_tuning(ctypes.c_int64(agg_max_entries), ctypes.c_int(fast_path)), "nsv_set_fused_tuning")

@@ -21,6 +21,8 @@
 //     gradient with vector reductions (red.global.add.v2.f32), and -- when poses are optimised --
 //     dL/dx through the grid, reduced per pixel and pushed through the Rodrigues VJP.
 // Nothing but the table gradient, O(weights) and O(slices) values is written to global memory.
+#include <stdlib.h>
+
 #include "inr_common.cuh"
 #include "mlp_mma.cuh"
 
@@ -67,7 +69,7 @@ struct Layout {
   // ---- byte offsets ----
   static constexpr size_t b_groups = (w_halves * 2 + 15) / 16 * 16;
   static constexpr size_t b_gfloats = b_groups + (size_t)NG * g_halves * 2;
-  static constexpr size_t b_lt = b_gfloats + (size_t)NG * g_floats * 4;
+  static constexpr size_t b_lt = (b_gfloats + (size_t)NG * g_floats * 4 + 15) / 16 * 16;
   static constexpr size_t b_acc = b_lt + lt_floats * 4;
   static constexpr size_t bytes = b_acc + (n_density + n_sigma) * 4;
 };
@@ -83,6 +85,7 @@ struct RenderLayout {
   static constexpr size_t f_base = (halves * 2 + 15) / 16 * 16;
   static constexpr size_t fz0 = 0;
   static constexpr size_t flt = fz0 + kTile;
+  static_assert(flt % 4 == 0, "LevelTable must stay 16-byte aligned");
   static constexpr size_t bytes = f_base + (flt + (sizeof(LevelTable) + 3) / 4) * 4;
 };
 
@@ -156,13 +159,7 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_kernel(const __grid_con
       stage_weights(swt + L::wso, L::ldh, ws + (size_t)W * kIn, kOutP, W);
     }
     for (int i = tid; i < (int)(L::n_density + L::n_sigma); i += kThreads) sacc[i] = 0.f;
-    if (tid < kIn / 2) {
-      lt.scale[tid] = cfg.grid.scale[tid];
-      lt.res[tid] = cfg.grid.res[tid];
-      lt.size[tid] = cfg.grid.size[tid];
-      lt.offset[tid] = cfg.grid.offset[tid];
-      lt.hashed[tid] = cfg.grid.hashed[tid];
-    }
+    stage_level_table(lt, cfg.grid, tid, a.agg_max, a.fast, a.table, a.g_table);
   }
   // ---- log-sum-exp of logit_coef (slice scale c_k = n_s softmax_k), per warp (n_slices is small) ----
   float lse = 0.f;
@@ -210,9 +207,11 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_kernel(const __grid_con
         xn[i] = (xw[i] - cfg.bbox_lo[i]) / (cfg.bbox_hi[i] - cfg.bbox_lo[i]);
       }
     }
+    bool slow;
     {
       __half* xrow = sh + L::sx + (size_t)srow * L::ldx;
-      encode_warp(xn, lt, cfg.grid.n_levels, a.table, [&](int l, __half2 v) { *reinterpret_cast<__half2*>(xrow + 2 * l) = v; });
+      slow = encode_warp(xn, lt, cfg.grid.n_levels, a.table, [&](int l, __half2 v) { *reinterpret_cast<__half2*>(xrow + 2 * l) = v; },
+                         [&](int c, uint4 v) { *reinterpret_cast<uint4*>(xrow + 8 * c) = v; });
     }
     __syncwarp();
 
@@ -437,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_kernel(const __grid_con
     auto fetch = [&](int l) { return make_float2(grow_s[2 * l], grow_s[2 * l + 1]); };
     if (cfg.pose_grad) {
       float gx[3];
-      scatter_warp<true>(xn, lt, cfg.grid.n_levels, a.table, fetch, inv_gscale, a.g_table, gx);
+      scatter_warp<true>(xn, lt, cfg.grid.n_levels, a.table, fetch, inv_gscale, a.g_table, gx, slow);
       float gwd[3], part[12];
 #pragma unroll
       for (int i = 0; i < 3; ++i) gwd[i] = xb ? 0.f : gx[i] / (cfg.bbox_hi[i] - cfg.bbox_lo[i]);  // one lane per sample contributes
@@ -472,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_kernel(const __grid_con
       }
     } else {
       float gx[3];
-      scatter_warp<false>(xn, lt, cfg.grid.n_levels, a.table, fetch, inv_gscale, a.g_table, gx);
+      scatter_warp<false>(xn, lt, cfg.grid.n_levels, a.table, fetch, inv_gscale, a.g_table, gx, slow);
     }
   }
 
@@ -529,13 +528,7 @@ __global__ void __launch_bounds__(kThreads, 1) inr_render_kernel(const __grid_co
   for (int l = 0; l + 1 < DEPTH; ++l) stage_weights(sh + L::wdh + (size_t)l * W * L::ldh, L::ldh, wd + (size_t)W * kIn + (size_t)l * W * W, W, W);
   stage_weights(sh + L::wdo, L::ldh, wd + (size_t)W * kIn + (size_t)(DEPTH - 1) * W * W, kOutP, W);
   LevelTable& lt = *reinterpret_cast<LevelTable*>(sf + L::flt);
-  if (tid < kIn / 2) {
-    lt.scale[tid] = cfg.grid.scale[tid];
-    lt.res[tid] = cfg.grid.res[tid];
-    lt.size[tid] = cfg.grid.size[tid];
-    lt.offset[tid] = cfg.grid.offset[tid];
-    lt.hashed[tid] = cfg.grid.hashed[tid];
-  }
+  stage_level_table(lt, cfg.grid, tid, 0u, 1, a.table, nullptr);
   __syncthreads();
   const int64_t total = a.M * (int64_t)a.S;
   const int64_t n_tiles = (total + kTile - 1) / kTile;
@@ -570,7 +563,8 @@ __global__ void __launch_bounds__(kThreads, 1) inr_render_kernel(const __grid_co
     }
     {
       __half* xrow = sh + L::sx + (size_t)srow * L::ldx;
-      encode_warp(xn, lt, cfg.grid.n_levels, a.table, [&](int l, __half2 v) { *reinterpret_cast<__half2*>(xrow + 2 * l) = v; });
+      encode_warp(xn, lt, cfg.grid.n_levels, a.table, [&](int l, __half2 v) { *reinterpret_cast<__half2*>(xrow + 2 * l) = v; },
+                         [&](int c, uint4 v) { *reinterpret_cast<uint4*>(xrow + 8 * c) = v; });
     }
     __syncwarp();
     uint32_t ain[1][kIn / 16][4];
@@ -679,7 +673,17 @@ int launch_render(const RenderArgs& a, cudaStream_t st) {
 }  // namespace fused
 }  // namespace nsv
 
-namespace nsv { namespace fused { static int g_fused_impl = 0; } }
+namespace nsv { namespace fused {
+static int g_fused_impl = 0;
+static long g_agg_max = -1;  // -1: NSV_AGG_MAX or the built-in default
+static int g_fast_path = -1;
+} }
+
+extern "C" int nsv_set_fused_tuning(int64_t agg_max_entries, int fast_path) {
+  nsv::fused::g_agg_max = agg_max_entries < 0 ? -1 : (long)agg_max_entries;
+  nsv::fused::g_fast_path = fast_path < 0 ? -1 : (fast_path != 0);
+  return NSV_OK;
+}
 
 extern "C" int nsv_set_fused_impl(int impl) {
   if (impl < 0 || impl > 2) {
@@ -764,6 +768,12 @@ extern "C" int nsv_inr_train_step(const nsv_inr_config* cfg, const nsv_inr_param
   a.log2S = log2S;
   a.off_density = ml.off_density;
   a.off_sigma = ml.off_sigma;
+  {  // tuning knobs (read once): NSV_AGG_MAX = largest dense level (entries) whose gradient is pre-reduced per warp
+    static const long agg_env = getenv("NSV_AGG_MAX") ? atol(getenv("NSV_AGG_MAX")) : (long)kAggDefault;
+    static const int fast_env = getenv("NSV_FAST_PATH") ? atoi(getenv("NSV_FAST_PATH")) : 1;
+    a.agg_max = (uint32_t)(g_agg_max >= 0 ? g_agg_max : (agg_env < 0 ? 0 : agg_env));
+    a.fast = g_fast_path >= 0 ? g_fast_path : fast_env;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const bool sig = cfg->pixel_variance != 0;
   if (g_fused_impl != 1) {  // tcgen05 / TMEM implementation when it is instantiated for this configuration

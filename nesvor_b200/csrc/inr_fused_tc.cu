@@ -134,13 +134,7 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
       umma::stage_tile(wt + L::ws0, ws, 64, 32, tid, kThreads);
       umma::stage_tile(wt + L::wso, ws + 64 * 32, 16, 64, tid, kThreads);
     }
-    if (tid < kIn / 2) {
-      lt.scale[tid] = cfg.grid.scale[tid];
-      lt.res[tid] = cfg.grid.res[tid];
-      lt.size[tid] = cfg.grid.size[tid];
-      lt.offset[tid] = cfg.grid.offset[tid];
-      lt.hashed[tid] = cfg.grid.hashed[tid];
-    }
+    stage_level_table(lt, cfg.grid, tid, a.agg_max, a.fast, a.table, a.g_table);
     if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
       umma::mbar_init(reinterpret_cast<uint64_t*>(smem + L::b_sync), 1);
@@ -242,8 +236,9 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
         xn[i] = (xw[i] - cfg.bbox_lo[i]) / (cfg.bbox_hi[i] - cfg.bbox_lo[i]);
       }
     }
-    encode_warp(xn, lt, cfg.grid.n_levels, a.table,
-                [&](int l, __half2 v) { *reinterpret_cast<__half2*>(gt + L::tx + umma::tile_off(srow, 2 * l, 32)) = v; });
+    const bool slow = encode_warp(xn, lt, cfg.grid.n_levels, a.table,
+                [&](int l, __half2 v) { *reinterpret_cast<__half2*>(gt + L::tx + umma::tile_off(srow, 2 * l, 32)) = v; },
+                [&](int c, uint4 v) { *reinterpret_cast<uint4*>(gt + L::tx + umma::tile_off(srow, 8 * c, 32)) = v; });
     publish();
 
     // ================= phase 1: density MLP forward on tcgen05 =================
@@ -496,26 +491,27 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
     }
     wait_mma();
     acc_on = 1u;
-    // dL/d(features): fp32 [128][32], element (r, c) at r*32 + (c ^ (r & 31)) -- conflict-free for both the
-    // row-per-lane epilogue writes and the sample-pair reads of the scatter
+    // dL/d(features): fp32 [128][32], feature pair (2l, 2l+1) of row r at r*32 + ((2l) ^ ((r & 15) << 1)) -- 8-byte
+    // accesses, conflict-free for both the row-per-lane epilogue writes and the sample-pair reads of the scatter
     float* sdx = reinterpret_cast<float*>(gt + (L::alias_dx ? L::th + (size_t)(DEPTH - 1) * 128 * 64 * 2 : L::dx));
     {
       uint32_t d[16];
       umma::tmem_ld16(td + tlane + 16 * half, d);
       umma::tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 16; ++c) sdx[erow * 32 + ((16 * half + c) ^ (erow & 31))] = __uint_as_float(d[c]);
+      for (int c = 0; c < 16; c += 2)
+        *reinterpret_cast<float2*>(&sdx[erow * 32 + ((16 * half + c) ^ ((erow & 15) << 1))]) =
+            make_float2(__uint_as_float(d[c]), __uint_as_float(d[c + 1]));
     }
     umma::fence_before_sync();
     group_barrier(grp, kGT);
     // ---- scatter into the table gradient (+ pose gradient), lane pair = sample ----
     auto fetch = [&](int l) {
-      const int sw = srow & 31;
-      return make_float2(sdx[srow * 32 + ((2 * l) ^ sw)], sdx[srow * 32 + ((2 * l + 1) ^ sw)]);
+      return *reinterpret_cast<const float2*>(&sdx[srow * 32 + ((2 * l) ^ ((srow & 15) << 1))]);
     };
     if (cfg.pose_grad) {
       float gx[3];
-      scatter_warp<true>(xn, lt, cfg.grid.n_levels, a.table, fetch, inv_gscale, a.g_table, gx);
+      scatter_warp<true>(xn, lt, cfg.grid.n_levels, a.table, fetch, inv_gscale, a.g_table, gx, slow);
       float gwd[3], part[12];
 #pragma unroll
       for (int i = 0; i < 3; ++i) gwd[i] = xb ? 0.f : gx[i] / (cfg.bbox_hi[i] - cfg.bbox_lo[i]);
@@ -539,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
       }
     } else {
       float gx[3];
-      scatter_warp<false>(xn, lt, cfg.grid.n_levels, a.table, fetch, inv_gscale, a.g_table, gx);
+      scatter_warp<false>(xn, lt, cfg.grid.n_levels, a.table, fetch, inv_gscale, a.g_table, gx, slow);
     }
     group_barrier(grp, kGT);  // the group's tiles (incl. the aliased dX slot) are free for the next tile
   }

@@ -221,3 +221,57 @@ def test_fused_rejects_unsupported(native_lib):
     model, _ = build_pair(make_args(), 4)
     with pytest.raises(FusedUnsupported):
         FusedState(model.inr, args, model)
+
+
+@pytest.fixture
+def fused_tuning():
+    from nesvor_b200 import _lib
+
+    yield _lib.set_fused_tuning
+    _lib.set_fused_tuning(-1, -1)
+
+
+def _run_fused(args, model, batch):
+    from nesvor_b200.nesvor.fused import FusedState
+
+    xyz, v, idx, noise = batch
+    st = FusedState(model.inr, args, model, n_batch_samples=args.batch_size * args.n_samples)
+    st.grad.zero_()
+    losses, v_out = st.forward_backward(xyz.cuda(), v.cuda(), idx.cuda(), noise.cuda(), want_v_out=True)
+    torch.cuda.synchronize()
+    return st, losses.clone(), v_out
+
+
+@pytest.mark.parametrize("name", ["cfg2_density_only", "default_all_heads"])
+def test_fused_fast_loops_match_generic_loops(native_lib, name, fused_tuning):
+    """The chunked branch-free gather / scatter (+ warp pre-reduction of coarse-level gradients) against the
+    generic per-level loops: rendered pixels bit-identical, gradients equal up to float-atomic ordering."""
+    args = make_args(**CONFIGS[name])
+    model, _ = build_pair(args, 9)
+    batch = make_batch(args, 9)
+    fused_tuning(0, 0)  # generic loops, no pre-reduction: every contribution is its own atomic
+    st0, l0, v0 = _run_fused(args, model, batch)
+    for agg, fast in ((8192, 1), (0, 1), (1 << 20, 1), (8192, 0)):
+        fused_tuning(agg, fast)
+        st1, l1, v1 = _run_fused(args, model, batch)
+        assert torch.equal(v0, v1), (agg, fast)
+        assert rel_l2(st1.grad[: st1.n_total].cpu(), st0.grad[: st0.n_total].cpu()) < 2e-5, (agg, fast)
+        if not args.no_transformation_optimization:
+            assert rel_l2(st1.seg("axisangle", st1.grad).cpu(), st0.seg("axisangle", st0.grad).cpu()) < 1e-4, (agg, fast)
+
+
+@pytest.mark.parametrize("fast", [0, 1])
+def test_fused_out_of_box_samples(native_lib, fast, fused_tuning):
+    """Samples outside the bounding box index wrapped (mod T_l) entries, tcnn-style: the fast
+    loops detect them per warp and fall back to the generic loops; both must agree with the oracle."""
+    args = make_args(**CONFIGS["cfg2_density_only"])
+    model, om = build_pair(args, 9)
+    xyz, v, idx, noise = make_batch(args, 9, extent=60.0 * 2.3)  # pixel centres spread over +-34.5 mm, box = +-30 mm
+    losses_o, aux = om.forward(xyz, v, idx, noise, return_aux=True)
+    om.total_loss({k: val for k, val in losses_o.items() if k != "transReg"}).backward()
+    fused_tuning(-1, fast)
+    st, losses, v_out = _run_fused(args, model, (xyz, v, idx, noise))
+    err = rel_l2(v_out.cpu(), aux["v_out"].detach())
+    print(f"out-of-box [fast={fast}]: rel-L2(v_out) = {err:.3e}")
+    assert err <= V_OUT_TOL
+    assert rel_l2(st.seg("table", st.grad).cpu(), om.P["table"].grad) < 2e-2

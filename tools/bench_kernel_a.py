@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Kernel-A-only timing sweep over the gather/scatter tuning hooks (BASELINE config 2 by default).
+
+    python tools/bench_kernel_a.py [--variants "agg:fast,agg:fast,..."] [--reps 20] [--cfg 2|3]
+
+Prints one line per variant: mean / min kernel time (CUDA events, L2 flushed between launches)."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--variants", default="8192:1,0:1,0:0,8192:0,40000:1,300000:1")
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--cfg", type=int, default=2)
+    ap.add_argument("--impl", default="auto")
+    a = ap.parse_args()
+    import torch
+
+    import bench
+    from nesvor_b200 import _lib
+    from nesvor_b200.csrc import build as nsv_build
+
+    nsv_build.build()
+    import nesvor_b200 as nb
+    from nesvor_b200.data.phantom import simulate_slices
+    from nesvor_b200.nesvor.fused import FusedTrainer
+    from nesvor_b200.nesvor.train import Dataset
+
+    dev = torch.device("cuda", 0)
+    _lib.set_fused_impl(a.impl)
+    if a.cfg == 2:
+        args = bench.make_args(dev)
+        n, n_stacks, kw = 128, 3, {}
+    else:  # config-3 heads: defaults (depth 1, sigma_net, slice variance, pose optimisation), S = 256
+        args = bench.make_args(dev, depth=1, no_pixel_variance=False, no_slice_variance=False, no_transformation_optimization=False,
+                               n_levels=None, n_samples=256, batch_size=4096)
+        n, n_stacks, kw = 128, 3, dict(motion_deg=3.0, motion_mm=1.5)
+    torch.manual_seed(0)
+    slices, _, _ = simulate_slices(n=n, n_stacks=n_stacks, res_r=1.0, res_s=1.0, gap=3.0, device=dev, **kw)
+    dataset = Dataset(slices, args)
+    model = nb.NeSVoR(dataset.transformation, dataset.resolution, dataset.mean, dataset.bounding_box, args)
+    trainer = FusedTrainer(model, args)
+    st = trainer.state
+    B, S = args.batch_size, args.n_samples
+    for _ in range(20):  # a few real iterations so that the table is not at its init
+        trainer.step(**dataset.get_batch(B, dev))
+    batch = dataset.get_batch(B, dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    for var in a.variants.split(","):
+        agg, fast = (int(x) for x in var.split(":"))
+        _lib.set_fused_tuning(agg, fast)
+        durs = []
+        for i in range(3 + a.reps):
+            flush.zero_()
+            st.grad.zero_()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record(stream)
+            st.forward_backward(batch["xyz"], batch["v"], batch["slice_idx"], None, seed=0, offset=i * B * S)
+            k1.record(stream)
+            torch.cuda.synchronize()
+            if i >= 3:
+                durs.append(k0.elapsed_time(k1))
+        print(json.dumps({"cfg": a.cfg, "impl": a.impl, "agg_max": agg, "fast": fast, "ms_mean": sum(durs) / len(durs), "ms_min": min(durs),
+                          "gq_per_s": B * S / (min(durs) * 1e-3) / 1e9}), flush=True)
+    _lib.set_fused_tuning(-1, -1)
+
+
+if __name__ == "__main__":
+    main()
