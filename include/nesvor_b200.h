@@ -196,13 +196,17 @@ typedef struct nsv_inr_grads {    /* device pointers, all fp32, caller zero-fill
 int64_t nsv_inr_mlp_layout(const nsv_inr_config* h_cfg, int64_t* h_offsets /* [3]: density, sigma, bias */);
 
 /* which implementation of kernel A nsv_inr_train_step uses: 0 = auto (tcgen05/TMEM when instantiated for the
- * configuration, else mma.sync), 1 = mma.sync fragments, 2 = tcgen05/TMEM only (NSV_EUNSUPPORTED otherwise) */
+ * configuration, else mma.sync), 1 = mma.sync fragments, 2 = tcgen05/TMEM, all warps run every phase,
+ * 3 = tcgen05/TMEM warp-specialised (memory warps + chain warps, opt-in); 2 and 3 return NSV_EUNSUPPORTED otherwise */
 int nsv_set_fused_impl(int impl);
 /* tuning / test hooks of kernel A's gather and scatter loops (no reference counterpart; results are identical up to
  * float-atomic ordering): `agg_max_entries` = largest dense level whose gradient is pre-reduced inside a warp before
  * touching global memory (0 = never, < 0 = default: every dense level, or $NSV_AGG_MAX); `fast_path` = 0 forces the generic
  * per-level loops, 1 the chunked branch-free loops, < 0 = default (1 or $NSV_FAST_PATH). */
 int nsv_set_fused_tuning(int64_t agg_max_entries, int fast_path);
+/* profiling hook: 16 int64 device counters that the tcgen05 kernel A (config-2 instantiation) fills with per-phase
+ * warp cycles (gather, barriers, MMA wait, epilogues, losses, scatter, pixel barrier, -); NULL switches it off */
+int nsv_set_fused_timers(void* device_counters);
 
 int nsv_inr_train_step(const nsv_inr_config* h_cfg, const nsv_inr_params* h_params, const nsv_inr_grads* h_grads,
                        const float* xyz /* [B,3] */, const float* v /* [B] */, const int64_t* slice_idx /* [B] */,

@@ -140,7 +140,7 @@ def make_grid_meta(n_levels: int, n_features: int, log2_hashmap_size: int, base_
     return m, int(total)
 
 
-FUSED_IMPLS = {"auto": 0, "mma": 1, "tcgen05": 2}
+FUSED_IMPLS = {"auto": 0, "mma": 1, "tcgen05": 2, "ws": 3}
 
 
 def set_fused_impl(name: str) -> None:

@@ -28,6 +28,7 @@ SOURCES = {
     "mlp.cu": [],
     "inr_fused.cu": [],
     "inr_fused_tc.cu": [],
+    "inr_fused_ws.cu": [],
     "adamw.cu": [],
     "umma_selftest.cu": [],
 }

@@ -33,13 +33,13 @@ struct LevelTable {
   uint32_t n_dense;   // levels [0, n_dense) are dense, [n_dense, n_levels) hashed
   uint32_t fast_ok;   // the branch-free loops apply to this grid
   uint32_t agg_last;  // dense levels with size - 1 <= agg_last pre-reduce their gradient inside the warp
-  uint32_t pad_;
+  uint32_t ablate;    // profiling only (NSV_ABLATE): bit 0 skips the table loads, bit 1 the table reductions, bit 2 the MLP chain
 };
 static_assert(sizeof(FastLevel) == 16 && sizeof(LevelTable) % 16 == 0, "LevelTable layout");
 
 // executed by the first kIn/2 threads of the CTA (followed by a CTA barrier at the call site)
 __device__ __forceinline__ void stage_level_table(LevelTable& lt, const nsv_grid_meta& m, int tid, uint32_t agg_max, int fast,
-                                                  const __half* table, float* g_table) {
+                                                  const __half* table, float* g_table, uint32_t ablate = 0u) {
   if (tid < kIn / 2) {
     lt.scale[tid] = m.scale[tid];
     lt.res[tid] = m.res[tid];
@@ -64,7 +64,7 @@ __device__ __forceinline__ void stage_level_table(LevelTable& lt, const nsv_grid
     lt.n_dense = (uint32_t)nd;
     lt.fast_ok = ok ? 1u : 0u;
     lt.agg_last = agg_max ? agg_max - 1u : 0u;
-    lt.pad_ = 0u;
+    lt.ablate = ablate;
   }
 }
 struct FusedArgs {
@@ -93,6 +93,8 @@ struct FusedArgs {
   int64_t B;
   int S, log2S;
   int64_t off_density, off_sigma;
+  uint32_t ablate;   // profiling only: see LevelTable::ablate
+  long long* timers; // profiling only: 8 per-phase warp-cycle counters (device memory) or NULL
   uint32_t agg_max;  // tuning: warp-level gradient pre-reduction for dense levels with at most this many entries (0: off)
   int fast;          // tuning: 0 forces the generic (branchy) gather / scatter loops
 };
@@ -359,8 +361,13 @@ __device__ __forceinline__ uint32_t encode_chunk(const float xn[3], const LevelT
     } else {
       fast_entries<true>(fl, g[0] + xb, g[1], g[2], e);
     }
+    if (lt.ablate & 1u) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) raw[i][q] = ldg_u32(tl + e[q]);
+      for (int q = 0; q < 4; ++q) raw[i][q] = e[q] & 0x03ff03ffu;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) raw[i][q] = ldg_u32(tl + e[q]);
+    }
   }
   uint32_t packed[4];
 #pragma unroll
@@ -509,6 +516,7 @@ __device__ __forceinline__ void scatter_chunk(const float xn[3], const LevelTabl
       p[2 * q + 1] = wt[q] * g1;
     }
     float* gl = lt.grd[l];
+    if (lt.ablate & 2u) continue;
     if (i < ND && lt.fast[l].last <= lt.agg_last) {
       scatter_aggregated(lt.fast[l], e[i], p, gl, lane, xb);
     } else {
@@ -596,6 +604,8 @@ static __global__ void __launch_bounds__(256) inr_finalize_kernel(const float* _
 
 // implemented in inr_fused_tc.cu; returns NSV_EUNSUPPORTED when the configuration has no tcgen05 instantiation
 int launch_train_tc(const FusedArgs& a, cudaStream_t st);
+// implemented in inr_fused_ws.cu (warp-specialised tcgen05 kernel); same contract
+int launch_train_ws(const FusedArgs& a, cudaStream_t st);
 
 }  // namespace fused
 }  // namespace nsv

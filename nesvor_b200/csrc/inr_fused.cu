@@ -677,7 +677,13 @@ namespace nsv { namespace fused {
 static int g_fused_impl = 0;
 static long g_agg_max = -1;  // -1: NSV_AGG_MAX or the built-in default
 static int g_fast_path = -1;
+static long long* g_timers = nullptr;
 } }
+
+extern "C" int nsv_set_fused_timers(void* device_counters) {
+  nsv::fused::g_timers = (long long*)device_counters;
+  return NSV_OK;
+}
 
 extern "C" int nsv_set_fused_tuning(int64_t agg_max_entries, int fast_path) {
   nsv::fused::g_agg_max = agg_max_entries < 0 ? -1 : (long)agg_max_entries;
@@ -686,8 +692,8 @@ extern "C" int nsv_set_fused_tuning(int64_t agg_max_entries, int fast_path) {
 }
 
 extern "C" int nsv_set_fused_impl(int impl) {
-  if (impl < 0 || impl > 2) {
-    nsv::set_error("nsv_set_fused_impl: 0 = auto, 1 = mma.sync, 2 = tcgen05");
+  if (impl < 0 || impl > 3) {
+    nsv::set_error("nsv_set_fused_impl: 0 = auto, 1 = mma.sync, 2 = tcgen05, 3 = tcgen05 warp-specialised");
     return NSV_EINVAL;
   }
   nsv::fused::g_fused_impl = impl;
@@ -773,9 +779,12 @@ extern "C" int nsv_inr_train_step(const nsv_inr_config* cfg, const nsv_inr_param
     static const int fast_env = getenv("NSV_FAST_PATH") ? atoi(getenv("NSV_FAST_PATH")) : 1;
     a.agg_max = (uint32_t)(g_agg_max >= 0 ? g_agg_max : (agg_env < 0 ? 0 : agg_env));
     a.fast = g_fast_path >= 0 ? g_fast_path : fast_env;
+    a.timers = g_timers;
+    a.ablate = getenv("NSV_ABLATE") ? (uint32_t)atoi(getenv("NSV_ABLATE")) : 0u;  // profiling only, tcgen05 kernel
   }
   cudaStream_t st = (cudaStream_t)stream;
   const bool sig = cfg->pixel_variance != 0;
+  if (g_fused_impl == 3) return launch_train_ws(a, st);  // warp-specialised variant: opt-in (not faster yet, profiles/r01_phase_breakdown.md)
   if (g_fused_impl != 1) {  // tcgen05 / TMEM implementation when it is instantiated for this configuration
     const int rc = launch_train_tc(a, st);
     if (rc != NSV_EUNSUPPORTED || g_fused_impl == 2) return rc;

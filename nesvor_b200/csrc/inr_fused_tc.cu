@@ -104,9 +104,21 @@ __device__ __forceinline__ void epi_mask_store(uint32_t taddr, unsigned char* ti
   }
 }
 
-template <int DEPTH, bool SIGMA>
+// TIMED (profiling builds only, a.timers != NULL): every warp accumulates the clock cycles it spends per phase
+// (0 geometry + gather, 1 publish / group barriers, 2 MMA issue -> mbarrier wait, 3 epilogues, 4 render + losses,
+//  5 scatter, 6 pixel barrier) and adds them to a.timers[phase] at the end
+template <int DEPTH, bool SIGMA, bool TIMED = false>
 __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_constant__ FusedArgs a) {
   using L = TcLayout<DEPTH, SIGMA>;
+  long long t_acc[TIMED ? 8 : 1] = {};
+  long long t_last = TIMED ? clock64() : 0;
+  auto tick = [&](int seg) {
+    if (TIMED) {
+      const long long t = clock64();
+      t_acc[seg] += t - t_last;
+      t_last = t;
+    }
+  };
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = warp >> 3, gw = warp & 7, row0 = gw * 16;
@@ -134,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
       umma::stage_tile(wt + L::ws0, ws, 64, 32, tid, kThreads);
       umma::stage_tile(wt + L::wso, ws + 64 * 32, 16, 64, tid, kThreads);
     }
-    stage_level_table(lt, cfg.grid, tid, a.agg_max, a.fast, a.table, a.g_table);
+    stage_level_table(lt, cfg.grid, tid, a.agg_max, a.fast, a.table, a.g_table, a.ablate);
     if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
       umma::mbar_init(reinterpret_cast<uint64_t*>(smem + L::b_sync), 1);
@@ -191,14 +203,17 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
   };
   // writers publish their shared-memory stores to the tensor core, then the group meets
   auto publish = [&]() {
+    tick(3);
     umma::fence_smem_to_async();
     umma::fence_before_sync();
     group_barrier(grp, kGT);
+    tick(1);
   };
   auto wait_mma = [&]() {
     umma::mbar_wait(mbar, ph);
     ph ^= 1u;
     umma::fence_after_sync();
+    tick(2);
   };
 
   float loss_d = 0.f, loss_s = 0.f, loss_i = 0.f;
@@ -212,6 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
 
   for (int64_t tile = (int64_t)blockIdx.x * kNGroups + grp; tile < n_tiles; tile += (int64_t)gridDim.x * kNGroups) {
     // ================= phase 0: sample geometry + encoding (lane pair = sample) =================
+    tick(1);
     const int64_t sidx = tile * kGR + srow;
     const int64_t p = sidx >> a.log2S;
     const int j = (int)(sidx & (S - 1));
@@ -239,8 +255,9 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
     const bool slow = encode_warp(xn, lt, cfg.grid.n_levels, a.table,
                 [&](int l, __half2 v) { *reinterpret_cast<__half2*>(gt + L::tx + umma::tile_off(srow, 2 * l, 32)) = v; },
                 [&](int c, uint4 v) { *reinterpret_cast<uint4*>(gt + L::tx + umma::tile_off(srow, 8 * c, 32)) = v; });
+    tick(0);
     publish();
-
+    if (!(a.ablate & 4u)) {
     // ================= phase 1: density MLP forward on tcgen05 =================
     if (issuer) {
       umma::fence_after_sync();
@@ -324,8 +341,10 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
         sf[L::flv + grp * kGR + erow] = __uint_as_float(z[0]);
       }
     }
+    tick(3);
     umma::fence_before_sync();
     group_barrier(grp, kGT);  // z0 / log_var of every row are in shared memory
+    tick(1);
 
     // ================= phase 2: render, losses, gradients w.r.t. z0 / log_var (lane pair = sample) =================
     const float z0 = sf[L::fz0 + crow];
@@ -345,7 +364,9 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
         sf[L::fred + warp * 2 + 1] = s_u;
       }
     }
+    tick(4);
     pixel_barrier();
+    tick(6);
     float m_pix = 0.f, q_pix = 0.f;
     {
       const int w0 = (warp / wpp) * wpp;
@@ -406,6 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
       *reinterpret_cast<uint4*>(gt + L::tg + umma::tile_off(srow, 8, 16)) = make_uint4(0u, 0u, 0u, 0u);
     }
     if (wide) cta_barrier_all();  // the partner group has finished reading this group's rho / xw rows
+    tick(4);
     publish();
 
     // ================= phase 3: backward on tcgen05 =================
@@ -490,11 +512,12 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
       umma::commit(mbar);
     }
     wait_mma();
+    }
     acc_on = 1u;
     // dL/d(features): fp32 [128][32], feature pair (2l, 2l+1) of row r at r*32 + ((2l) ^ ((r & 15) << 1)) -- 8-byte
     // accesses, conflict-free for both the row-per-lane epilogue writes and the sample-pair reads of the scatter
     float* sdx = reinterpret_cast<float*>(gt + (L::alias_dx ? L::th + (size_t)(DEPTH - 1) * 128 * 64 * 2 : L::dx));
-    {
+    if (!(a.ablate & 4u)) {
       uint32_t d[16];
       umma::tmem_ld16(td + tlane + 16 * half, d);
       umma::tmem_ld_wait();
@@ -503,8 +526,10 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
         *reinterpret_cast<float2*>(&sdx[erow * 32 + ((16 * half + c) ^ ((erow & 15) << 1))]) =
             make_float2(__uint_as_float(d[c]), __uint_as_float(d[c + 1]));
     }
+    tick(3);
     umma::fence_before_sync();
     group_barrier(grp, kGT);
+    tick(1);
     // ---- scatter into the table gradient (+ pose gradient), lane pair = sample ----
     auto fetch = [&](int l) {
       return *reinterpret_cast<const float2*>(&sdx[srow * 32 + ((2 * l) ^ ((srow & 15) << 1))]);
@@ -537,7 +562,13 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
       float gx[3];
       scatter_warp<false>(xn, lt, cfg.grid.n_levels, a.table, fetch, inv_gscale, a.g_table, gx, slow);
     }
+    tick(5);
     group_barrier(grp, kGT);  // the group's tiles (incl. the aliased dX slot) are free for the next tile
+  }
+  if (TIMED) {
+    tick(1);
+    if (lane == 0 && a.timers)
+      for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(a.timers) + i, (unsigned long long)t_acc[i]);
   }
 
   // ================= epilogue: weight gradients TMEM -> global, losses =================
@@ -600,7 +631,12 @@ int launch_tc(const FusedArgs& a, cudaStream_t st) {
   }
   const int64_t ctas = (a.B * (int64_t)a.S / kGR + kNGroups - 1) / kNGroups;
   const int grid = (int)(ctas < num_sms() ? ctas : num_sms());
-  inr_train_tc_kernel<DEPTH, SIGMA><<<grid, kThreads, L::bytes, st>>>(a);
+  if (a.timers && DEPTH == 3 && !SIGMA) {  // profiling build of the config-2 instantiation
+    cudaFuncSetAttribute(inr_train_tc_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcLayout<3, false>::bytes);
+    inr_train_tc_kernel<3, false, true><<<grid, kThreads, L::bytes, st>>>(a);
+  } else {
+    inr_train_tc_kernel<DEPTH, SIGMA><<<grid, kThreads, L::bytes, st>>>(a);
+  }
   if (int err = check_launch("nsv_inr_train_step(tcgen05)")) return err;
   inr_finalize_kernel<<<1, 256, 0, st>>>(a.logit_coef, a.g_c, a.losses, a.n_slices, a.cfg.slice_scale, a.cfg.image_reg, a.cfg.delta);
   return check_launch("nsv_inr_train_step(finalize)");

@@ -111,13 +111,13 @@ def fused_impl(request):
     _lib.set_fused_impl("auto")
 
 
-@pytest.mark.parametrize("fused_impl", ["mma", "tcgen05"], indirect=True)
+@pytest.mark.parametrize("fused_impl", ["mma", "tcgen05", "ws"], indirect=True)
 @pytest.mark.parametrize("name", list(CONFIGS))
 def test_fused_train_step_parity(native_lib, name, fused_impl):
     from nesvor_b200.nesvor.fused import FusedState
 
-    if fused_impl == "tcgen05" and CONFIGS[name].get("width", 64) != 64:
-        pytest.skip("tcgen05 path is instantiated for width 64 (UMMA M = 64 wgrad)")
+    if fused_impl in ("tcgen05", "ws") and CONFIGS[name].get("width", 64) != 64:
+        pytest.skip("tcgen05 paths are instantiated for width 64 (UMMA M = 64 wgrad)")
     args = make_args(**CONFIGS[name])
     n_slices = 9
     model, om = build_pair(args, n_slices)

@@ -36,11 +36,14 @@ def _native_all(c, interp):
     return {k: v.cpu() for k, v in out.items()}
 
 
-def _tol(key):
+def _tol(key, ref=None):
     if key in ("slices", "weight") or key.endswith("grad_slices"):
         return GATHER_TOL
     if key.endswith("grad_tf"):
-        return dict(atol=2e-3, rtol=2e-4)  # sums of O(1e2..1e4) terms reduced in a different order
+        # sums of O(1e2..1e4) terms reduced by float atomics in a different order: the error of a sum is set by its
+        # largest terms, not by each element's own value (the fp32 and fp64 oracles differ by ~3e-6 of the scale)
+        scale = float(np.abs(np.asarray(ref)).max()) if ref is not None else 0.0
+        return dict(atol=2e-3 + 1e-5 * scale, rtol=2e-4)
     return SCATTER_TOL
 
 
@@ -54,7 +57,7 @@ def test_against_reference_kernel_outputs(native_lib, tag, kw, interp):
         if k == "adjbwd1_grad_slices":  # gathers an equalized (scatter-produced) grad_vol: round-off, not bits
             torch.testing.assert_close(v, ref, atol=2e-4, rtol=2e-4, msg=lambda m: f"{k}: {m}")
         else:
-            torch.testing.assert_close(v, ref, **_tol(k), msg=lambda m: f"{k}: {m}")
+            torch.testing.assert_close(v, ref, **_tol(k, ref), msg=lambda m: f"{k}: {m}")
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -65,7 +68,7 @@ def test_against_oracle_seeded(native_lib, oracle, dtype):
         c = slice_acq_case(seed=21, dtype=dtype, masks=True, D=33, H=29, W=31, n=7, h=37, w=35)
         got, ref = _native_all(c, interp), _run_all(oracle, c, interp)
         for k, v in got.items():
-            tol = _tol(k) if dtype == np.float32 else dict(atol=1e-10, rtol=1e-9)
+            tol = _tol(k, ref[k]) if dtype == np.float32 else dict(atol=1e-10, rtol=1e-9)
             if k == "adjbwd1_grad_slices" and dtype == np.float32:
                 tol = dict(atol=2e-4, rtol=2e-4)
             torch.testing.assert_close(v, torch.from_numpy(ref[k]), **tol, msg=lambda m: f"{k} interp={interp}: {m}")

@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--cfg", type=int, default=2)
     ap.add_argument("--impl", default="auto")
+    ap.add_argument("--ablate", default="0", help="comma list of NSV_ABLATE masks (1: no table loads, 2: no table reductions, 4: no MLP chain)")
+    ap.add_argument("--timers", action="store_true", help="per-phase warp-cycle breakdown of the tcgen05 kernel (profiling build)")
     a = ap.parse_args()
     import torch
 
@@ -53,7 +55,9 @@ def main():
     batch = dataset.get_batch(B, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
-    for var in a.variants.split(","):
+    for var in [(v, ab) for v in a.variants.split(",") for ab in a.ablate.split(",")]:
+        var, ablate = var
+        os.environ["NSV_ABLATE"] = ablate
         agg, fast = (int(x) for x in var.split(":"))
         _lib.set_fused_tuning(agg, fast)
         durs = []
@@ -67,9 +71,31 @@ def main():
             torch.cuda.synchronize()
             if i >= 3:
                 durs.append(k0.elapsed_time(k1))
-        print(json.dumps({"cfg": a.cfg, "impl": a.impl, "agg_max": agg, "fast": fast, "ms_mean": sum(durs) / len(durs), "ms_min": min(durs),
+        print(json.dumps({"cfg": a.cfg, "impl": a.impl, "agg_max": agg, "fast": fast, "ablate": int(ablate), "ms_mean": sum(durs) / len(durs), "ms_min": min(durs),
                           "gq_per_s": B * S / (min(durs) * 1e-3) / 1e9}), flush=True)
     _lib.set_fused_tuning(-1, -1)
+    if a.timers:
+        import ctypes
+
+        os.environ["NSV_ABLATE"] = "0"
+        counters = torch.zeros(16, dtype=torch.int64, device=dev)
+        _lib.lib().nsv_set_fused_timers(ctypes.c_void_p(counters.data_ptr()))
+        n = 10
+        for i in range(n):
+            flush.zero_()
+            st.grad.zero_()
+            st.forward_backward(batch["xyz"], batch["v"], batch["slice_idx"], None, seed=0, offset=i * B * S)
+        torch.cuda.synchronize()
+        _lib.lib().nsv_set_fused_timers(ctypes.c_void_p(0))
+        c = [float(x) for x in counters.cpu()]
+        if a.impl == "ws":
+            mem = dict(zip(["gather", "wait_x_empty", "scatter", "wait_dx_full"], [x / (n * 148 * 16) for x in c[:4]]))
+            chain = dict(zip(["wait_x_full", "mma_wait", "epilogues", "barriers", "losses", "wait_dx_empty"], [x / (n * 148 * 8) for x in c[8:14]]))
+            print(json.dumps({"mem_warp_cycles": mem, "mem_total": sum(mem.values()), "chain_warp_cycles": chain, "chain_total": sum(chain.values())}), flush=True)
+        else:
+            names = ["gather", "barriers", "mma_wait", "epilogues", "losses", "scatter", "pixel_barrier", "-"]
+            per_warp = [x / (n * 148 * 16) for x in c[:8]]
+            print(json.dumps({"phase_cycles_per_warp": dict(zip(names, per_warp)), "total": sum(per_warp)}), flush=True)
 
 
 if __name__ == "__main__":
