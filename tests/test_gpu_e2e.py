@@ -1,0 +1,101 @@
+"""End-to-end GPU test of the path's callers: simulated stacks -> Dataset -> train()
+with the fused kernel -> Dataset.mask -> sample_volume / sample_slices on the forward-only fused renderer.
+Reference flow: nesvor/nesvor/train.py:123-232, sample.py:10-64."""
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools"))
+
+
+@pytest.fixture(scope="module")
+def trained(native_lib):
+    import nesvor_b200 as nb
+    import psnr_phantom as pp
+    from nesvor_b200.data.phantom import simulate_slices
+
+    dev = torch.device("cuda", 0)
+    # the synthetic stacks are lattice-aligned (pixel centres on half-integers): round() piles them into every other
+    # voxel, which lifts the reference's count-based mask threshold above the blurred counts -> use a lower threshold
+    args = pp.make_args(dev, n_iter=2000, batch_size=2048, n_samples=64, mask_threshold=0.1, no_loss_sync=True,
+                        output_resolution=1.0, inference_batch_size=1 << 14, n_inference_samples=128, no_output_psf=False)
+    torch.manual_seed(0)
+    slices, volume, _ = simulate_slices(device=dev, n=48, n_stacks=3, res_r=1.0, res_s=1.0, gap=2.0)
+    inr, out_slices, mask = nb.train(slices, args)
+    return dict(args=args, slices=slices, volume=volume, inr=inr, out_slices=out_slices, mask=mask)
+
+
+def test_train_returns_model_slices_and_mask(trained):
+    t = trained
+    assert len(t["out_slices"]) == len(t["slices"])
+    m = t["mask"]
+    frac = float(m.mask.float().mean())
+    assert 0.02 < frac < 0.9, frac  # the head, not nothing and not the whole padded box
+    # the mask covers the phantom's support
+    import psnr_phantom as pp
+
+    grid = pp.phantom_grid(48, 1.0).to(m.image.device)
+    inside = t["volume"][0, 0].reshape(-1) > 0
+    cover = (m.sample_points(grid)[inside] > 0).float().mean()
+    assert cover > 0.95, float(cover)
+
+
+def test_sample_volume_reconstructs_phantom(trained):
+    import psnr_phantom as pp
+    from nesvor_b200.nesvor.sample import sample_points, sample_volume
+
+    t = trained
+    vol = sample_volume(t["inr"], t["mask"], t["args"])
+    assert torch.isfinite(vol.image).all() and int(vol.mask.sum()) > 0 and float(vol.image.max()) > 0.1
+    grid = pp.phantom_grid(48, 1.0).to(vol.image.device)
+    gt = t["volume"][0, 0].reshape(-1)
+    import copy
+
+    a = copy.copy(t["args"])
+    a.no_output_psf = True
+    rec = sample_points(t["inr"], grid, a)
+    p_in = pp.psnr(rec.cpu(), gt.cpu(), (gt > 0).cpu())
+    print("PSNR inside phantom after 2000 iterations:", p_in)
+    assert p_in > 14.0
+
+
+def test_sample_slices_fit_the_data(trained):
+    from nesvor_b200.nesvor.sample import sample_slices
+
+    t = trained
+    sel = t["out_slices"][:: max(len(t["out_slices"]) // 6, 1)]
+    sim = sample_slices(t["inr"], sel, t["mask"], t["args"])
+    num = den = 0.0
+    for s, r in zip(sel, sim):
+        m = s.mask & r.mask
+        assert r.image.shape == s.image.shape
+        num += float(((r.image[m] - s.image[m]) ** 2).sum())
+        den += float((s.image[m] ** 2).sum())
+    rel = (num / max(den, 1e-30)) ** 0.5
+    print("relative L2 of re-simulated slices vs input slices:", rel)
+    assert den > 0 and rel < 0.35
+
+
+def test_fused_and_unfused_renderers_agree(trained):
+    """sample_points through nsv_inr_render (in-kernel Philox noise) vs INR.sample_batch + INR.forward (torch.randn):
+    same estimator, different noise -> agreement at Monte-Carlo accuracy; without PSF they agree at fp16 accuracy."""
+    import copy
+
+    from nesvor_b200.nesvor.sample import sample_points
+
+    t = trained
+    dev = t["mask"].image.device
+    xyz = (torch.rand(4096, 3, device=dev) - 0.5) * 30.0
+    a_f, a_u = copy.copy(t["args"]), copy.copy(t["args"])
+    a_u.fused = False
+    a_f.n_inference_samples = a_u.n_inference_samples = 512  # Monte-Carlo error ~ 1 / sqrt(S)
+    for no_psf, tol in ((True, 2e-3), (False, 6e-2)):
+        a_f.no_output_psf = a_u.no_output_psf = no_psf
+        vf, vu = sample_points(t["inr"], xyz, a_f), sample_points(t["inr"], xyz, a_u)
+        rel = float((vf - vu).norm() / vu.norm())
+        print("fused vs unfused renderer, no_output_psf =", no_psf, "rel-L2 =", rel)
+        assert rel < tol
