@@ -68,7 +68,20 @@ def _compile(src, flags, force, verbose):
 
 
 def build(force=False, verbose=False):
+    """Idempotent and safe to call from several processes at once (one rank per GPU): an exclusive file lock serialises
+    the builders, objects are compiled only when their sources changed, and the library is replaced atomically."""
+    import fcntl
+
     os.makedirs(OBJ_DIR, exist_ok=True)
+    with open(os.path.join(OBJ_DIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     srcs = {s: fl for s, fl in SOURCES.items() if os.path.exists(os.path.join(HERE, s))}
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         results = list(ex.map(lambda kv: _compile(kv[0], kv[1], force, verbose), srcs.items()))
@@ -77,10 +90,12 @@ def build(force=False, verbose=False):
         if r[2]:
             print(r[2])
     if any(r[1] for r in results) or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        tmp = f"{LIB}.tmp.{os.getpid()}"
+        cmd = [NVCC, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        os.replace(tmp, LIB)
     return LIB
 
 
