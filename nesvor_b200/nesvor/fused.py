@@ -139,6 +139,31 @@ class FusedState:
         self.psf_sigma = model.psf_sigma.contiguous().float() if model is not None else None
         self.pull_from_model()
 
+    # ------------------------------------------------------------------ data-parallel peer memory
+    def enable_peer_memory(self, group) -> None:
+        """Moves the gradient buffer and the fp16 parameter copy into ONE symmetric allocation (CUDA peer memory set up
+        by torch.distributed._symmetric_memory over NVLink) and records every rank's pointers, so that
+        nsv_adamw_step_dp can read all ranks' gradients and write all ranks' fp16 parameters directly."""
+        import torch.distributed._symmetric_memory as symm_mem
+
+        n_grad = self.grad.numel() * 4
+        n_grad_pad = (n_grad + 255) // 256 * 256
+        nbytes = n_grad_pad + self.flat16.numel() * 2
+        buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+        handle = symm_mem.rendezvous(buf, group)
+        grad = buf[:n_grad].view(torch.float32)
+        flat16 = buf[n_grad_pad:nbytes].view(torch.float16)
+        grad.zero_()
+        flat16.copy_(self.flat16)
+        self.grad, self.flat16 = grad, flat16
+        self.losses = self.grad[self.n_total : self.n_total + 8]
+        self._symm_buf, self.peer_handle = buf, handle
+        world = handle.world_size
+        ptrs = [int(p) for p in handle.buffer_ptrs]
+        self.peer_grads = (ctypes.c_void_p * world)(*ptrs)
+        self.peer_flat16 = (ctypes.c_void_p * world)(*[p + n_grad_pad for p in ptrs])
+        handle.barrier()  # every rank's copy is initialised before anyone's optimiser writes into it
+
     # ------------------------------------------------------------------ model <-> flat
     def seg(self, name: str, buf: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         if name not in self.offsets:
@@ -253,6 +278,27 @@ class FusedTrainer:
         self.iteration = 0
         self.seed = int(getattr(args, "seed", 0) or 0)
         self.pose = not args.no_transformation_optimization
+        self.dp_mode: Optional[str] = None  # set on the first distributed step: "peer" (fused kernel) or "allreduce" (NCCL / gloo)
+
+    def _setup_dp(self, dist, world: int) -> None:
+        """Chooses the data-parallel optimiser path: the fused reduce-scatter + AdamW + all-gather kernel over NVLink
+        peer memory when the ranks are GPUs of one node with symmetric memory available, else all-reduce + AdamW
+        (`args.dp_optimizer` = "peer" | "allreduce" forces one; a forced "peer" raises if peer memory cannot be set up)."""
+        want = getattr(self.args, "dp_optimizer", "auto")
+        mode = "allreduce"
+        if want in ("auto", "peer") and world > 1 and self.state.device.type == "cuda" and dist.get_backend() == "nccl" and world <= 16:
+            try:
+                self.state.enable_peer_memory(dist.group.WORLD)
+                mode = "peer"
+            except Exception as e:  # symmetric memory unavailable (no peer access, old driver, ...)
+                if want == "peer":
+                    raise
+                import logging
+
+                logging.warning("peer-memory optimiser unavailable (%s); using NCCL all-reduce + AdamW", e)
+        elif want == "peer":
+            raise RuntimeError("dp_optimizer='peer' needs NCCL ranks on CUDA devices (world <= 16)")
+        self.dp_mode = mode
 
     def decay_lr(self, gamma: float) -> None:
         self.lr *= gamma
@@ -291,6 +337,8 @@ class FusedTrainer:
         the flat gradient of the trainable prefix is summed with ONE NCCL all-reduce, and the mean over
         ranks is folded into AdamW's unscale factor, so all replicas apply the identical update."""
         st, a = self.state, self.args
+        if self.dp_mode is None:
+            self._setup_dp(dist, world)
         self.iteration += 1
         st.losses.zero_()
         n_q = xyz.shape[0] * a.n_samples
@@ -300,6 +348,28 @@ class FusedTrainer:
         out = st.loss_dict(losses.clone())
         if self.pose and a.weight_transformation:
             out[T_REG] = self._trans_reg()  # identical on every rank: the all-reduce mean leaves it unchanged
+        self._dp_update(dist, world)
+        return out
+
+    def _dp_update(self, dist, world: int) -> None:
+        """Mean of the ranks' gradients + AdamW + refreshed fp16 parameters on every rank; clears the gradient."""
+        st = self.state
+        rank = dist.get_rank()
+        if self.dp_mode is None:
+            self._setup_dp(dist, world)
+        if self.dp_mode == "peer":
+            h = st.peer_handle
+            h.barrier()  # every rank's kernel A has finished: all gradients are complete
+            with torch.cuda.device(st.device):
+                rc = _lib.lib().nsv_adamw_step_dp(
+                    _lib.ptr(st.flat), st.peer_grads, _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), st.peer_flat16,
+                    ctypes.c_int(world), ctypes.c_int(rank), ctypes.c_int64(st.n_train), ctypes.c_float(self.lr), ctypes.c_float(0.9),
+                    ctypes.c_float(0.99), ctypes.c_float(1e-15), ctypes.c_float(1e-2), ctypes.c_int(self.iteration),
+                    ctypes.c_float(1.0 / world), _lib.stream(st.device))
+            _lib.check(rc, "nsv_adamw_step_dp")
+            h.barrier()  # every owner has read this rank's gradient and written this rank's fp16 parameters
+            st.grad[: st.n_train].zero_()
+            return
         from .distributed import allreduce_gradient
 
         unscale = allreduce_gradient(st.grad[: st.n_train], dist, world)
@@ -309,9 +379,17 @@ class FusedTrainer:
                 ctypes.c_int64(st.n_train), ctypes.c_float(self.lr), ctypes.c_float(0.9), ctypes.c_float(0.99), ctypes.c_float(1e-15),
                 ctypes.c_float(1e-2), ctypes.c_int(self.iteration), ctypes.c_float(unscale), ctypes.c_int(1), _lib.stream(st.device))
         _lib.check(rc, "nsv_adamw_step")
-        return out
 
     def sync_to_model(self) -> None:
+        if self.dp_mode == "peer":  # every rank holds only its own shard of the fp32 master: collect the others
+            import torch.distributed as dist
+
+            st, world = self.state, dist.get_world_size()
+            lo, hi = ctypes.c_int64(), ctypes.c_int64()
+            for r in range(world):
+                _lib.lib().nsv_adamw_shard_bounds(ctypes.c_int64(st.n_train), ctypes.c_int(world), ctypes.c_int(r), ctypes.byref(lo), ctypes.byref(hi))
+                if hi.value > lo.value:
+                    dist.broadcast(st.flat[lo.value : hi.value], src=r)
         self.state.push_to_model()
 
 

@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""2+-rank check of the fused data-parallel optimiser (reduce-scatter + AdamW + all-gather over NVLink peer memory,
+nsv_adamw_step_dp) against NCCL all-reduce + nsv_adamw_step: both trainers start from identical parameters and see
+identical per-rank batches and PSF noise; after a few iterations the fp16 parameters every rank trains with and the
+gathered fp32 master must agree (bit-identical for 2 ranks: a + b has one summation order).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/dp_check.py
+"""
+import copy
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+    import nesvor_b200 as nb
+    import psnr_phantom as pp
+    from nesvor_b200.data.phantom import simulate_slices
+    from nesvor_b200.nesvor.fused import FusedTrainer
+    from nesvor_b200.nesvor.train import Dataset
+
+    args = pp.make_args(dev, batch_size=1024, n_samples=64, no_transformation_optimization=False)  # every head + pose gradient
+    torch.manual_seed(0)
+    slices, _, _ = simulate_slices(device=dev, n=48, n_stacks=3, res_r=1.0, res_s=1.0, gap=2.0, motion_deg=2.0, motion_mm=1.0)
+    dataset = Dataset(slices, args)
+    trainers = {}
+    for mode in ("peer", "allreduce"):
+        torch.manual_seed(7)  # identical initial parameters on every rank and for both trainers
+        model = nb.NeSVoR(dataset.transformation, dataset.resolution, dataset.mean, dataset.bounding_box, args)
+        a = copy.copy(args)
+        a.dp_optimizer = mode
+        trainers[mode] = FusedTrainer(model, a)
+    g = torch.Generator().manual_seed(100 + rank)
+    P = dataset.xyz.shape[0]
+    tp, ta = trainers["peer"], trainers["allreduce"]
+    for it in range(6):
+        sel = torch.randint(0, P, (args.batch_size,), generator=g).to(dev)
+        noise = torch.randn(args.batch_size, args.n_samples, 3, generator=g).to(dev)
+        batch = dict(xyz=dataset.xyz[sel], v=dataset.v[sel], slice_idx=dataset.slice_idx[sel])
+        # kernel A accumulates with float atomics (run-to-run round-off that Adam's normalisation amplifies), so the two
+        # optimiser paths are compared on the SAME per-rank gradient: one forward / backward, copied into both trainers
+        for tr in (tp, ta):
+            tr.iteration += 1
+            tr.state.losses.zero_()
+        ta.state.forward_backward(batch["xyz"], batch["v"], batch["slice_idx"], noise)
+        if it == 0:
+            tp._setup_dp(dist, world)
+        tp.state.grad[: tp.state.n_total].copy_(ta.state.grad[: ta.state.n_total])
+        for tr in (tp, ta):
+            tr._dp_update(dist, world)
+        # the next forward must see the same parameters in both trainers (checked at the end); keep them in lockstep
+    torch.cuda.synchronize()
+    assert tp.dp_mode == "peer" and ta.dp_mode == "allreduce", (tp.dp_mode, ta.dp_mode)
+    n = tp.state.n_train
+    d16 = (tp.state.flat16[:n].float() - ta.state.flat16[:n].float()).abs().max().item()
+    changed = (tp.state.flat16[:n] != 0).float().mean().item()
+    tp.sync_to_model()
+    ta.sync_to_model()
+    d32 = (tp.state.flat[:n] - ta.state.flat[:n]).abs().max().item()
+    scale = ta.state.flat[:n].abs().max().item()
+    # every rank must hold the same fp16 parameters
+    ref = tp.state.flat16[:n].clone()
+    dist.broadcast(ref, src=0)
+    same = bool((ref == tp.state.flat16[:n]).all())
+    out = dict(rank=rank, world=world, max_abs_diff_fp16=d16, max_abs_diff_fp32_master=d32, param_scale=scale, replicas_identical=same,
+               nonzero_frac=changed)
+    print(json.dumps(out), flush=True)
+    ok = same and d16 <= (0.0 if world == 2 else 2e-3 * scale) and d32 <= (0.0 if world == 2 else 1e-4 * scale)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
