@@ -257,7 +257,8 @@ def run_ours(a):
         hb = host[i % len(host)]
         batch = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
         out = one_step(batch)
-        loss_host = {k: float(v) for k, v in out.items()}  # D2H read of the step's losses (syncs, like train.py:199-200)
+        vals = torch.stack([v.reshape(()) for v in out.values()]).tolist()  # ONE D2H read of the step's losses (syncs, like train.py:199-200)
+        loss_host = dict(zip(out.keys(), vals))
     e1.record()
     sync_all()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)

@@ -3,7 +3,7 @@
 Public surface = the reference's (daviddmc/NeSVoR @ f110505) names for this path:
     build_encoding, build_network, INR (= INRModel), NeSVoR, train, sample_volume, sample_points,
     sample_slice, sample_slices, slice_acquisition, slice_acquisition_adjoint, axisangle2mat,
-    mat2axisangle, RigidTransform, get_PSF, resolution2sigma.
+    mat2axisangle, RigidTransform, get_PSF, resolution2sigma, and (svort/srr.py) CG, SRR, PSFreconstruction.
 All compute runs in libnesvor_b200.so (nesvor_b200/csrc, C ABI in include/nesvor_b200.h); there is
 no CPU or pure-PyTorch fallback.
 """
@@ -14,5 +14,7 @@ from .utils import get_PSF, resolution2sigma
 from .image import Slice, Volume
 from .nesvor import (INR, INRModel, NeSVoR, build_encoding, build_network, train, Dataset, sample_volume, sample_points,
                      sample_slice, sample_slices)
+
+from .svort import CG, SRR, PSFreconstruction
 
 __version__ = "0.1.0"

@@ -10,19 +10,43 @@
 namespace nsv {
 namespace {
 
+// 4 elements per thread and iteration (16-byte accesses; `n4` vectors, then a scalar tail): the pass is pure streaming
+// (16 B read + 12..18 B written per element) and needs wide accesses to approach HBM bandwidth
+__device__ __forceinline__ void adamw_update(float g, float& pi, float& mi, float& vi, float lr, float b1, float b2, float eps, float wd,
+                                             float step_size, float inv_sqrt_bc2, float unscale) {
+  g *= unscale;
+  pi *= 1.f - lr * wd;
+  mi = b1 * mi + (1.f - b1) * g;
+  vi = b2 * vi + (1.f - b2) * g * g;
+  const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+  pi -= step_size * (mi / denom);
+}
+
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, __half* __restrict__ p16, int64_t n, float lr, float b1,
                                                     float b2, float eps, float wd, float step_size, float inv_sqrt_bc2,
                                                     float unscale, int zero_grad) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float gi = g[i] * unscale;
-    float pi = p[i];
-    float mi = m[i], vi = v[i];
-    pi *= 1.f - lr * wd;
-    mi = b1 * mi + (1.f - b1) * gi;
-    vi = b2 * vi + (1.f - b2) * gi * gi;
-    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
-    pi -= step_size * (mi / denom);
+  const int64_t n4 = n >> 2;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < n4; i += nth) {
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 pv = reinterpret_cast<const float4*>(p)[i], mv = reinterpret_cast<const float4*>(m)[i], vv = reinterpret_cast<const float4*>(v)[i];
+    adamw_update(gv.x, pv.x, mv.x, vv.x, lr, b1, b2, eps, wd, step_size, inv_sqrt_bc2, unscale);
+    adamw_update(gv.y, pv.y, mv.y, vv.y, lr, b1, b2, eps, wd, step_size, inv_sqrt_bc2, unscale);
+    adamw_update(gv.z, pv.z, mv.z, vv.z, lr, b1, b2, eps, wd, step_size, inv_sqrt_bc2, unscale);
+    adamw_update(gv.w, pv.w, mv.w, vv.w, lr, b1, b2, eps, wd, step_size, inv_sqrt_bc2, unscale);
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (p16) {
+      const __half2 h0 = __floats2half2_rn(pv.x, pv.y), h1 = __floats2half2_rn(pv.z, pv.w);
+      reinterpret_cast<uint2*>(p16)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    }
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t i = 4 * n4 + tid; i < n; i += nth) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    adamw_update(g[i], pi, mi, vi, lr, b1, b2, eps, wd, step_size, inv_sqrt_bc2, unscale);
     p[i] = pi;
     m[i] = mi;
     v[i] = vi;
@@ -161,7 +185,9 @@ extern "C" int nsv_adamw_step(float* param, float* grad, float* exp_avg, float* 
   NSV_REQUIRE(param && grad && exp_avg && exp_avg_sq, "nsv_adamw_step: NULL pointer");
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   const float step_size = (float)((double)lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
-  const int64_t blocks = (n + 255) / 256;
+  NSV_REQUIRE(((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16 == 0 && (uintptr_t)param_f16 % 8 == 0,
+              "nsv_adamw_step: buffers must be 16-byte aligned (fp16 copy: 8-byte)");
+  const int64_t blocks = (n / 4 + 255) / 256 + 1;
   const int grid = (int)(blocks < (int64_t)num_sms() * 8 ? blocks : (int64_t)num_sms() * 8);
   adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, (__half*)param_f16, n, lr, beta1, beta2, eps,
                                                        weight_decay, step_size, inv_sqrt_bc2, grad_unscale, zero_grad);

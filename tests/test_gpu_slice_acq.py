@@ -100,24 +100,6 @@ def test_edge_cases(native_lib):
     np.testing.assert_allclose(float((gv * d).sum()), float(((o2 - out.detach()) * g).sum() / eps), rtol=1e-5)
 
 
-def _cg(A, b, x0, n_iter, tol):  # nesvor/svort/srr.py:12-34
-    x, r = x0, b - A(x0)
-    p, rr, i = r, torch.dot(r.flatten(), r.flatten()), 0
-    while True:
-        Ap = A(p)
-        alpha = rr / torch.dot(p.flatten(), Ap.flatten())
-        x = x + alpha * p
-        i += 1
-        if i == n_iter:
-            return x
-        r = r - alpha * Ap
-        rr_new = torch.dot(r.flatten(), r.flatten())
-        if rr_new <= tol:
-            return x
-        p = r + (rr_new / rr) * p
-        rr = rr_new
-
-
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_cg_recovers_phantom_known_answer(native_lib, dtype):
     """The reference's only KAT for A / A^T (tests/slice_acquisition/test_slice_acq.py:76-81): CG
@@ -143,15 +125,25 @@ def test_cg_recovers_phantom_known_answer(native_lib, dtype):
     A = lambda x: nb.slice_acquisition(theta, x, None, None, psf, (ss, ss), res_s / res, False, False)
     At = lambda y: nb.slice_acquisition_adjoint(theta, psf, y, None, None, (vs, vs, vs), res_s / res, False, False)
     slices = A(volume)
-    rec = torch.relu(_cg(lambda x: At(A(x)), At(slices), volume, 20, 1e-8))
+    rec = torch.relu(nb.CG(lambda x: At(A(x)), At(slices), volume, 20, 1e-8))  # product solver (nesvor_b200/svort/srr.py)
     if dtype == torch.float64:
         torch.testing.assert_close(rec, volume, atol=3e-5, rtol=1e-5)
     else:
         torch.testing.assert_close(rec, volume, atol=2e-3, rtol=1e-5)
     # and a non-trivial start: 20 CG iterations from zero reduce the data residual by > 5x (measured ~10x)
-    rec0 = _cg(lambda x: At(A(x)), At(slices), torch.zeros_like(volume), 20, 0.0)
+    rec0 = nb.CG(lambda x: At(A(x)), At(slices), None, 20, 0.0)
     r0, r1 = float(slices.norm()), float((A(rec0) - slices).norm())
     assert r1 < 0.2 * r0, (r0, r1)
+    # the reference's module interface: PSFreconstruction -> SRR (svort/inference.py:420-444 usage)
+    params = dict(psf=psf, slice_shape=(ss, ss), volume_shape=(vs, vs, vs), res_s=res_s, res_r=res, interp_psf=False)
+    v0 = nb.PSFreconstruction(theta, slices, None, None, params)
+    assert v0.shape == volume.shape and torch.isfinite(v0).all()
+    r_psf = float((A(v0) - slices).norm())
+    v_cg = nb.SRR(n_iter=5, use_CG=True)(theta, slices, v0, params, slices_mask=slices > 0)
+    v_gd = nb.SRR(n_iter=5, use_CG=False, alpha=0.5, beta=0.02, delta=0.1)(theta, slices, v0.clone(), params)
+    r_cg, r_gd = float((A(v_cg) - slices).norm()), float((A(v_gd) - slices).norm())
+    print("data residual: PSF recon", r_psf, "-> 5 CG", r_cg, "| 5 gradient steps", r_gd, "of", r0)
+    assert r_cg < 0.5 * r_psf and r_gd < r_psf and float(v_cg.min()) >= 0.0
 
 
 def test_adjointness_at_baseline_size(native_lib):
