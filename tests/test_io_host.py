@@ -1,0 +1,80 @@
+"""Checkpoint round trip and reading a reference-style `model.pt` (nesvor/cli/io.py:36-59): pickled
+`nesvor.image.image.Volume` / `nesvor.transform.transform.RigidTransform` objects and tcnn-layout flat parameters
+(first MLP layer padded to 16 input columns).  Host logic only: no kernel runs."""
+import sys
+import types
+from argparse import Namespace
+
+import torch
+
+
+def _args(**kw):
+    a = dict(n_features_per_level=2, log2_hashmap_size=12, level_scale=2.0, coarsest_resolution=16.0, finest_resolution=8.0,
+             depth=1, width=32, n_features_z=15, single_precision=False, dtype=torch.float16, device=torch.device("cpu"))
+    a.update(kw)
+    return Namespace(**a)
+
+
+def test_save_load_round_trip(tmp_path):
+    from nesvor_b200.image import Volume
+    from nesvor_b200.io import load_model, save_model
+    from nesvor_b200.nesvor.models import INR
+    from nesvor_b200.transform import RigidTransform
+
+    args = _args()
+    bb = torch.tensor([[-30.0, -30.0, -30.0], [30.0, 30.0, 30.0]])
+    inr = INR(bb, args)
+    mask = Volume(torch.ones(4, 5, 6), torch.ones(4, 5, 6, dtype=torch.bool), RigidTransform(torch.zeros(1, 6)), 0.8, 0.8, 0.8)
+    path = str(tmp_path / "model.pt")
+    save_model(path, inr, mask, args)
+    inr2, mask2, args2 = load_model(path, torch.device("cpu"))
+    for k, v in inr.state_dict().items():
+        assert torch.equal(v, inr2.state_dict()[k]), k
+    assert torch.equal(mask2.mask, mask.mask) and mask2.resolution_x == 0.8 and args2.width == 32
+
+
+def test_reads_reference_style_checkpoint(tmp_path):
+    from nesvor_b200.io import load_model
+    from nesvor_b200.nesvor.models import INR
+
+    # stand-ins for the reference's classes, living under the reference's module paths while the file is written
+    mods = {n: types.ModuleType(n) for n in ("nesvor", "nesvor.image", "nesvor.image.image", "nesvor.transform", "nesvor.transform.transform")}
+
+    class RigidTransform:  # attribute names of nesvor/transform/transform.py:8-22
+        def __init__(self, ax):
+            self.trans_first, self._axisangle, self._matrix = True, ax, None
+
+    class Volume:  # attribute names of nesvor/image/image.py:17-42
+        def __init__(self, image, mask, transformation, r):
+            self.image, self.mask, self.transformation = image, mask, transformation
+            self.resolution_x = self.resolution_y = self.resolution_z = r
+
+    RigidTransform.__module__, RigidTransform.__qualname__ = "nesvor.transform.transform", "RigidTransform"
+    Volume.__module__, Volume.__qualname__ = "nesvor.image.image", "Volume"
+    mods["nesvor.transform.transform"].RigidTransform = RigidTransform
+    mods["nesvor.image.image"].Volume = Volume
+    sys.modules.update(mods)
+    try:
+        args = _args()
+        bb = torch.tensor([[-30.0, -30.0, -30.0], [30.0, 30.0, 30.0]])
+        ours = INR(bb, args)  # 2 levels x 2 features = 4 inputs: tcnn pads the first layer to 16 columns, this build to 32
+        n_table = ours.encoding.params.numel()
+        g = torch.Generator().manual_seed(0)
+        w0, w1 = torch.randn(32, 16, generator=g), torch.randn(16, 32, generator=g)
+        state = {"bounding_box": bb, "encoding.params": torch.randn(n_table, generator=g),
+                 "density_net.params": torch.cat([w0.reshape(-1), w1.reshape(-1)])}
+        mask = Volume(torch.ones(3, 3, 3), torch.ones(3, 3, 3, dtype=torch.bool), RigidTransform(torch.zeros(1, 6)), 1.0)
+        ref_args = Namespace(**{k: v for k, v in vars(args).items() if k not in ("dtype", "device")})
+        path = str(tmp_path / "ref_model.pt")
+        torch.save({"model": state, "mask": mask, "args": ref_args}, path)
+    finally:
+        for n in mods:
+            sys.modules.pop(n, None)
+    inr, mask2, merged = load_model(path, torch.device("cpu"))
+    from nesvor_b200.image import Volume as OurVolume
+    from nesvor_b200.transform import RigidTransform as OurRT
+
+    assert isinstance(mask2, OurVolume) and isinstance(mask2.transformation, OurRT) and merged.dtype == torch.float16
+    assert torch.equal(inr.encoding.params.detach(), state["encoding.params"])
+    v0, v1 = inr.density_net.weight_views()
+    assert torch.equal(v0[:, :16].detach(), w0) and float(v0[:, 16:].detach().abs().max()) == 0.0 and torch.equal(v1.detach(), w1)
