@@ -196,8 +196,9 @@ typedef struct nsv_inr_grads {    /* device pointers, all fp32, caller zero-fill
 int64_t nsv_inr_mlp_layout(const nsv_inr_config* h_cfg, int64_t* h_offsets /* [3]: density, sigma, bias */);
 
 /* which implementation of kernel A nsv_inr_train_step uses: 0 = auto (tcgen05/TMEM when instantiated for the
- * configuration, else mma.sync), 1 = mma.sync fragments, 2 = tcgen05/TMEM, all warps run every phase,
- * 3 = tcgen05/TMEM warp-specialised (memory warps + chain warps, opt-in); 2 and 3 return NSV_EUNSUPPORTED otherwise */
+ * configuration -- the warp-specialised kernel for the sigma_net heads, the all-phases kernel otherwise -- else mma.sync),
+ * 1 = mma.sync fragments, 2 = tcgen05/TMEM, all warps run every phase, 3 = tcgen05/TMEM warp-specialised (memory
+ * warps + chain warps); 2 and 3 return NSV_EUNSUPPORTED when not instantiated for the configuration */
 int nsv_set_fused_impl(int impl);
 /* tuning / test hooks of kernel A's gather and scatter loops (no reference counterpart; results are identical up to
  * float-atomic ordering): `agg_max_entries` = largest dense level whose gradient is pre-reduced inside a warp before

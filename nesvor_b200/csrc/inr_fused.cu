@@ -784,7 +784,13 @@ extern "C" int nsv_inr_train_step(const nsv_inr_config* cfg, const nsv_inr_param
   }
   cudaStream_t st = (cudaStream_t)stream;
   const bool sig = cfg->pixel_variance != 0;
-  if (g_fused_impl == 3) return launch_train_ws(a, st);  // warp-specialised variant: opt-in (not faster yet, profiles/r01_phase_breakdown.md)
+  // warp-specialised variant: measured faster where the MLP chain is short and wide in heads (reference defaults:
+  // depth 1 + sigma_net, 0.667 vs 0.771 ms at 2^20 queries), slower on the 3-hidden-layer config-2 model (0.74 vs 0.72 ms;
+  // profiles/r01_phase_breakdown.md) -> auto picks it for the sigma_net instantiation only
+  if (g_fused_impl == 3 || (g_fused_impl == 0 && sig)) {
+    const int rc = launch_train_ws(a, st);
+    if (rc != NSV_EUNSUPPORTED || g_fused_impl == 3) return rc;
+  }
   if (g_fused_impl != 1) {  // tcgen05 / TMEM implementation when it is instantiated for this configuration
     const int rc = launch_train_tc(a, st);
     if (rc != NSV_EUNSUPPORTED || g_fused_impl == 2) return rc;
