@@ -189,7 +189,8 @@ typedef struct nsv_inr_grads {    /* device pointers, all fp32, caller zero-fill
   float* slice_embedding;
   float* slice_scale_c;           /* [n_slices]: receives dL/dlogit_coef (softmax chain rule applied by the finalize kernel) */
   float* log_var_slice;
-  float* losses;                  /* [8]: [0] MSE, [1] logVar, [2] biasReg, [3] imageReg (final values) */
+  float* losses;                  /* [8]: [0] MSE, [1] logVar, [2] biasReg, [3] imageReg (final values);
+                                   * [4] INPUT when n_levels_bias > 0: mean(log_bias) over the whole batch, see nsv_inr_bias_mean */
 } nsv_inr_grads;
 
 /* number of fp16 elements of the packed MLP buffer and per-net offsets (host helper) */
@@ -213,6 +214,17 @@ int nsv_inr_train_step(const nsv_inr_config* h_cfg, const nsv_inr_params* h_para
                        const float* xyz /* [B,3] */, const float* v /* [B] */, const int64_t* slice_idx /* [B] */,
                        const float* noise /* [B,S,3] or NULL -> in-kernel Philox(seed, offset) */,
                        uint64_t seed, uint64_t offset, float* v_out /* [B] or NULL */, int64_t B, int S, void* stream);
+
+/* Bias-field head (b_net, nesvor/nesvor/models.py:247-258,344-347; n_levels_bias > 0).  biasReg = mean(log_bias)^2
+ * (models.py:323) couples every sample of the batch, so its mean must exist before kernel A back-propagates: this
+ * forward-only pre-pass evaluates b_net on exactly the samples nsv_inr_train_step will draw (same xyz / slice_idx / noise
+ * or Philox(seed, offset)) and ADDS mean(log_bias) to *out_mean (device float, caller zero-fills; normally
+ * grads.losses + 4).  Data-parallel callers average it over ranks between the two calls.  nsv_inr_train_step then reads
+ * grads.losses[4], applies w_bias * d(mean^2) in its backward pass and reports biasReg in losses[2].
+ * Instantiated for 1 <= n_levels_bias <= 4, F = 2, width 64, depth 1, n_features_slice 16 (else NSV_EUNSUPPORTED). */
+int nsv_inr_bias_mean(const nsv_inr_config* h_cfg, const nsv_inr_params* h_params, const float* xyz /* [B,3] */,
+                      const int64_t* slice_idx /* [B] */, const float* noise /* [B,S,3] or NULL */, uint64_t seed, uint64_t offset,
+                      float* out_mean, int64_t B, int S, void* stream);
 
 int nsv_inr_render(const nsv_inr_config* h_cfg, const nsv_inr_params* h_params,
                    const float* xyz /* [M,3] */, const float* mat /* [M,3,4] per-point or [1,3,4] or NULL */, int mat_per_point,

@@ -29,6 +29,7 @@ SOURCES = {
     "inr_fused.cu": [],
     "inr_fused_tc.cu": [],
     "inr_fused_ws.cu": [],
+    "inr_bias.cu": [],
     "adamw.cu": [],
     "umma_selftest.cu": [],
 }

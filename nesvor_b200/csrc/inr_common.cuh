@@ -92,7 +92,7 @@ struct FusedArgs {
   float* v_out;
   int64_t B;
   int S, log2S;
-  int64_t off_density, off_sigma;
+  int64_t off_density, off_sigma, off_bias;
   uint32_t ablate;   // profiling only: see LevelTable::ablate
   long long* timers; // profiling only: 8 per-phase warp-cycle counters (device memory) or NULL
   uint32_t agg_max;  // tuning: warp-level gradient pre-reduction for dense levels with at most this many entries (0: off)
@@ -564,7 +564,7 @@ __device__ __forceinline__ void red_shared(float* p, float v) {
 // softmax chain rule for the slice scale + final loss values (1 block)
 static __global__ void __launch_bounds__(256) inr_finalize_kernel(const float* __restrict__ logit_coef, float* __restrict__ g_c,
                                                            float* __restrict__ losses, int n_slices, int slice_scale, int image_reg,
-                                                           float delta) {
+                                                           float delta, int n_levels_bias = 0) {
   __shared__ float red[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (slice_scale) {
@@ -599,9 +599,12 @@ static __global__ void __launch_bounds__(256) inr_finalize_kernel(const float* _
     }
   }
   if (tid == 0 && image_reg == 2) losses[3] = delta * (losses[3] - 1.f);
+  if (tid == 0 && n_levels_bias) losses[2] = losses[4] * losses[4];  // biasReg = mean(log_bias)^2 (models.py:323); [4] = the batch mean
 }
 
 
+// implemented in inr_bias.cu: adds mean(log_bias) over the B x S samples to *out_mean (forward only, CUDA cores)
+int launch_bias_mean(const FusedArgs& a, float* out_mean, cudaStream_t st);
 // implemented in inr_fused_tc.cu; returns NSV_EUNSUPPORTED when the configuration has no tcgen05 instantiation
 int launch_train_tc(const FusedArgs& a, cudaStream_t st);
 // implemented in inr_fused_ws.cu (warp-specialised tcgen05 kernel); same contract

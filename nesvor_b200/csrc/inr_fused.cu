@@ -730,8 +730,11 @@ extern "C" int nsv_inr_train_step(const nsv_inr_config* cfg, const nsv_inr_param
     set_error("nsv_inr_train_step: fused path needs n_samples in {32,64,128,256} and B*S a multiple of the 128/256-sample tile (got B=%lld S=%d)", (long long)B, S);
     return NSV_EUNSUPPORTED;
   }
-  if (cfg->n_levels_bias != 0) {
-    set_error("nsv_inr_train_step: the bias-field head (n_levels_bias > 0) is not fused yet");
+  const bool bias_head = cfg->n_levels_bias != 0;
+  if (bias_head && (cfg->n_levels_bias < 0 || cfg->n_levels_bias > 4 || cfg->n_levels_bias > cfg->grid.n_levels || !cfg->pixel_variance ||
+                    cfg->width != 64 || g_fused_impl == 1 || g_fused_impl == 3)) {
+    set_error("nsv_inr_train_step: the fused bias-field head needs 1 <= n_levels_bias <= 4, the sigma_net heads on (pixel variance, "
+              "depth 1, n_features_slice 16), width 64 and the tcgen05 all-phases kernel");
     return NSV_EUNSUPPORTED;
   }
   if (cfg->pixel_variance && (cfg->depth != 1 || cfg->n_features_slice != 16 || cfg->n_features_z != 15)) {
@@ -774,6 +777,7 @@ extern "C" int nsv_inr_train_step(const nsv_inr_config* cfg, const nsv_inr_param
   a.log2S = log2S;
   a.off_density = ml.off_density;
   a.off_sigma = ml.off_sigma;
+  a.off_bias = ml.off_bias;
   {  // tuning knobs (read once): NSV_AGG_MAX = largest dense level (entries) whose gradient is pre-reduced per warp
     static const long agg_env = getenv("NSV_AGG_MAX") ? atol(getenv("NSV_AGG_MAX")) : (long)kAggDefault;
     static const int fast_env = getenv("NSV_FAST_PATH") ? atoi(getenv("NSV_FAST_PATH")) : 1;
@@ -787,6 +791,7 @@ extern "C" int nsv_inr_train_step(const nsv_inr_config* cfg, const nsv_inr_param
   // warp-specialised variant: measured faster where the MLP chain is short and wide in heads (reference defaults:
   // depth 1 + sigma_net, 0.667 vs 0.771 ms at 2^20 queries), slower on the 3-hidden-layer config-2 model (0.74 vs 0.72 ms;
   // profiles/r01_phase_breakdown.md) -> auto picks it for the sigma_net instantiation only
+  if (bias_head) return launch_train_tc(a, st);  // the one instantiation of the bias-field head (losses[4] = mean log_bias, see header)
   if (g_fused_impl == 3 || (g_fused_impl == 0 && sig)) {
     const int rc = launch_train_ws(a, st);
     if (rc != NSV_EUNSUPPORTED || g_fused_impl == 3) return rc;

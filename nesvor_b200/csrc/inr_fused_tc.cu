@@ -25,28 +25,36 @@ namespace {
 
 constexpr int kW = 64, kGR = 128, kGT = 256, kNGroups = 2;
 
-template <int DEPTH, bool SIGMA>
+template <int DEPTH, bool SIGMA, bool BIAS = false>
 struct TcLayout {
+  static_assert(!BIAS || (SIGMA && DEPTH == 1), "the fused bias-field head rides on the sigma_net instantiation (depth 1, slice embedding on)");
   // ---- CTA-shared canonical weight tiles (byte offsets) ----
   static constexpr size_t w0 = 0;                                         // [64][32]
   static constexpr size_t wh = w0 + 64 * 32 * 2;                          // (DEPTH-1) x [64][64]
   static constexpr size_t wo = wh + (size_t)(DEPTH - 1) * 64 * 64 * 2;    // [16][64]
   static constexpr size_t ws0 = wo + 16 * 64 * 2;                         // [64][32]
   static constexpr size_t wso = ws0 + (SIGMA ? 64 * 32 * 2 : 0);          // [16][64]
-  static constexpr size_t w_end = wso + (SIGMA ? 16 * 64 * 2 : 0);
+  static constexpr size_t wb0 = wso + (SIGMA ? 16 * 64 * 2 : 0);           // [64][32] b_net first layer: [slice embedding(16) | pe_bias(8) | 0]
+  static constexpr size_t wbo = wb0 + (BIAS ? 64 * 32 * 2 : 0);           // [16][64]
+  static constexpr size_t w_end = wbo + (BIAS ? 16 * 64 * 2 : 0);
   // ---- per-group canonical activation tiles (byte offsets from the group base) ----
   static constexpr size_t tx = 0;                                         // [128][32] encoded features
   static constexpr size_t th = tx + 128 * 32 * 2;                         // DEPTH x [128][64] hidden, later dZ
   static constexpr size_t tg = th + (size_t)DEPTH * 128 * 64 * 2;         // [128][16] dL/dz
   static constexpr size_t tsx = tg + 128 * 16 * 2;                        // [128][32] sigma_net input
   static constexpr size_t tsh = tsx + (SIGMA ? 128 * 32 * 2 : 0);         // [128][64] sigma_net hidden
+  static constexpr size_t tbx = tsh + (SIGMA ? 128 * 64 * 2 : 0);         // [128][32] b_net input
+  static constexpr size_t tbh = tbx + (BIAS ? 128 * 32 * 2 : 0);          // [128][64] b_net hidden, later dZb; dead after the bias pass
+  static constexpr size_t tgb = tbh + (BIAS ? 128 * 64 * 2 : 0);          // [128][16] dL/d(log_bias)
+  static constexpr size_t dxb = tgb + (BIAS ? 128 * 16 * 2 : 0);          // [128][8] fp32: dL/d(pe_bias) coming out of b_net
   static constexpr bool alias_dx = DEPTH >= 2;                            // dL/d(features) reuses the dead H_last slot
-  static constexpr size_t dx = tsh + (SIGMA ? 128 * 64 * 2 : 0);          // [128][32] fp32, XOR-swizzled
-  static constexpr size_t g_bytes = dx + (alias_dx ? 0 : 128 * 32 * 4);
+  static constexpr size_t dx = dxb + (BIAS ? 128 * 8 * 4 : 0);            // [128][32] fp32, XOR-swizzled (BIAS: the dead tbh slot)
+  static constexpr size_t g_bytes = dx + ((alias_dx || BIAS) ? 0 : 128 * 32 * 4);
   // ---- CTA-level fp32 scratch, indexed by CTA row (group * 128 + row) ----
   static constexpr size_t b_groups = (w_end + 127) / 128 * 128;
   static constexpr size_t b_scr = b_groups + kNGroups * g_bytes;
-  static constexpr size_t fz0 = 0, flv = 256, frho = 512, fxw = 768, fred = 768 + 768, fend = fred + 16 * 16;  // floats
+  static constexpr size_t fz0 = 0, flv = 256, frho = 512, fxw = 768, fred = 768 + 768, flb = fred + 16 * 16;  // floats
+  static constexpr size_t fend = flb + (BIAS ? 256 : 0);
   static constexpr size_t b_lt = b_scr + fend * 4;
   static constexpr size_t b_sync = (b_lt + sizeof(LevelTable) + 15) / 16 * 16;  // mbar[2], tmem slot, flags
   static constexpr size_t bytes = b_sync + 64;
@@ -57,7 +65,9 @@ struct TcLayout {
   static constexpr uint32_t c_wo = c_wh + 64 * (DEPTH - 1);               // dWo^T [64 x 16]
   static constexpr uint32_t c_ws0 = c_wo + 16;                            // dWs0  [64 x 32]
   static constexpr uint32_t c_wso = c_ws0 + 32;                           // dWso^T [64 x 16]
-  static constexpr uint32_t c_end = c_wso + 16;
+  static constexpr uint32_t c_wb0 = c_wso + 16;                           // dWb0  [64 x 32]
+  static constexpr uint32_t c_wbo = c_wb0 + 32;                           // dWbo^T [64 x 16]
+  static constexpr uint32_t c_end = c_wbo + 16;
   static_assert(c_end <= 512, "TMEM columns");
 };
 
@@ -107,9 +117,9 @@ __device__ __forceinline__ void epi_mask_store(uint32_t taddr, unsigned char* ti
 // TIMED (profiling builds only, a.timers != NULL): every warp accumulates the clock cycles it spends per phase
 // (0 geometry + gather, 1 publish / group barriers, 2 MMA issue -> mbarrier wait, 3 epilogues, 4 render + losses,
 //  5 scatter, 6 pixel barrier) and adds them to a.timers[phase] at the end
-template <int DEPTH, bool SIGMA, bool TIMED = false>
+template <int DEPTH, bool SIGMA, bool TIMED = false, bool BIAS = false>
 __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_constant__ FusedArgs a) {
-  using L = TcLayout<DEPTH, SIGMA>;
+  using L = TcLayout<DEPTH, SIGMA, BIAS>;
   long long t_acc[TIMED ? 8 : 1] = {};
   long long t_last = TIMED ? clock64() : 0;
   auto tick = [&](int seg) {
@@ -145,6 +155,11 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
       const __half* ws = a.mlp + a.off_sigma;
       umma::stage_tile(wt + L::ws0, ws, 64, 32, tid, kThreads);
       umma::stage_tile(wt + L::wso, ws + 64 * 32, 16, 64, tid, kThreads);
+    }
+    if (BIAS) {
+      const __half* wb = a.mlp + a.off_bias;
+      umma::stage_tile(wt + L::wb0, wb, 64, 32, tid, kThreads);
+      umma::stage_tile(wt + L::wbo, wb + 64 * 32, 16, 64, tid, kThreads);
     }
     stage_level_table(lt, cfg.grid, tid, a.agg_max, a.fast, a.table, a.g_table, a.ablate);
     if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
@@ -182,6 +197,10 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
   const uint32_t s_ws0 = umma::saddr(wt + L::ws0), s_wso = umma::saddr(wt + L::wso);
   const uint32_t s_tx = umma::saddr(gt + L::tx), s_th = umma::saddr(gt + L::th), s_tg = umma::saddr(gt + L::tg);
   const uint32_t s_tsx = umma::saddr(gt + L::tsx), s_tsh = umma::saddr(gt + L::tsh);
+  const uint32_t s_wb0 = umma::saddr(wt + L::wb0), s_wbo = umma::saddr(wt + L::wbo);
+  const uint32_t s_tbx = umma::saddr(gt + L::tbx), s_tbh = umma::saddr(gt + L::tbh), s_tgb = umma::saddr(gt + L::tgb);
+  // batch mean of log_bias (biasReg = mean^2, models.py:323), produced by nsv_inr_bias_mean before this launch
+  const float bias_mean = BIAS ? __ldg(a.losses + 4) : 0.f;
   constexpr uint32_t RG64 = 8 * 128, RG32 = 4 * 128, RG16 = 2 * 128;  // byte stride between 8-row groups of a tile
   // forward: D[128 x N] = A[128 x K] W[N x K]^T  (A, W K-major)
   auto mma_fwd = [&](uint32_t s_a, uint32_t rg_a, uint32_t s_w, uint32_t rg_w, int K, int N) {
@@ -302,7 +321,16 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
           *reinterpret_cast<uint4*>(gt + L::tsx + umma::tile_off(erow, 16 + 8 * i, 32)) = v;
         }
       }
-    } else if (SIGMA) {  // sigma_net input columns 0..15 = slice embedding of the row's slice
+      if (BIAS) {  // b_net input columns 16..23 = features of the first n_levels_bias levels (models.py:344-347), 24..31 = 0
+        uint4 f = *reinterpret_cast<const uint4*>(gt + L::tx + umma::tile_off(erow, 0, 32));
+        const int nb = cfg.n_levels_bias;
+        if (nb < 2) f.y = 0u;
+        if (nb < 3) f.z = 0u;
+        if (nb < 4) f.w = 0u;
+        *reinterpret_cast<uint4*>(gt + L::tbx + umma::tile_off(erow, 16, 32)) = f;
+        *reinterpret_cast<uint4*>(gt + L::tbx + umma::tile_off(erow, 24, 32)) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    } else if (SIGMA) {  // sigma_net (and b_net) input columns 0..15 = slice embedding of the row's slice
       const int64_t pe = (tile * kGR + erow) >> a.log2S;
       const float* se = a.slice_embedding + (size_t)a.slice_idx[pe] * 16;
 #pragma unroll
@@ -315,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
           pv[q] = *reinterpret_cast<const uint32_t*>(&h);
         }
         *reinterpret_cast<uint4*>(gt + L::tsx + umma::tile_off(erow, 8 * i, 32)) = v;
+        if (BIAS) *reinterpret_cast<uint4*>(gt + L::tbx + umma::tile_off(erow, 8 * i, 32)) = v;
       }
     }
     // ================= phase 1b: sigma MLP forward =================
@@ -341,6 +370,30 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
         sf[L::flv + grp * kGR + erow] = __uint_as_float(z[0]);
       }
     }
+    // ================= phase 1c: bias-field MLP forward (b_net, models.py:247-258,344-347) =================
+    if (BIAS) {
+      publish();
+      if (issuer) {
+        umma::fence_after_sync();
+        mma_fwd(s_tbx, RG32, s_wb0, RG32, 32, 64);
+        umma::commit(mbar);
+      }
+      wait_mma();
+      epi_relu_store(td + tlane + 32 * half, gt + L::tbh, erow, 32 * half);
+      publish();
+      if (issuer) {
+        umma::fence_after_sync();
+        mma_fwd(s_tbh, RG64, s_wbo, RG64, 64, 16);
+        umma::commit(mbar);
+      }
+      wait_mma();
+      if (half == 0) {
+        uint32_t z[16];
+        umma::tmem_ld16(td + tlane, z);
+        umma::tmem_ld_wait();
+        sf[L::flb + grp * kGR + erow] = __uint_as_float(z[0]);
+      }
+    }
     tick(3);
     umma::fence_before_sync();
     group_barrier(grp, kGT);  // z0 / log_var of every row are in shared memory
@@ -351,6 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
     const float rho = softplus_f(z0);
     const float lv = SIGMA ? sf[L::flv + crow] : 0.f;
     const float u = SIGMA ? expf(lv) : 1.f;
+    const float bias = BIAS ? expf(sf[L::flb + crow]) : 1.f;  // exp(log_bias); detached inside var (models.py:289-291,309)
     if (xb == 0) {
       sf[L::frho + crow] = rho;
       sf[L::fxw + 3 * crow] = xw[0];
@@ -358,7 +412,7 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
       sf[L::fxw + 3 * crow + 2] = xw[2];
     }
     {
-      const float s_rho = warp_sum(xb ? 0.f : rho), s_u = warp_sum(xb ? 0.f : u);
+      const float s_rho = warp_sum(xb ? 0.f : bias * rho), s_u = warp_sum(xb ? 0.f : bias * u);
       if (lane == 0) {
         sf[L::fred + warp * 2] = s_rho;
         sf[L::fred + warp * 2 + 1] = s_u;
@@ -386,8 +440,10 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
     const float e = vhat - a.v[p];
     const float d_vhat = e / var * invB;
     const float d_var = (SIGMA || cfg.slice_variance) ? (0.5f / var - 0.5f * e * e / (var * var)) * invB : 0.f;
-    float d_rho = ck * d_vhat * invS;
-    const float d_lv = SIGMA ? (u * invS) * ck * 2.f * r * d_var : 0.f;
+    float d_rho = ck * d_vhat * invS * bias;
+    const float d_lv = SIGMA ? (bias * u * invS) * ck * 2.f * r * d_var : 0.f;
+    // v_out path + biasReg = mean(log_bias)^2 over the whole batch (weight w_bias)
+    const float d_lb = BIAS ? ck * d_vhat * invS * bias * rho + cfg.w_bias * 2.f * bias_mean * invB * invS : 0.f;
     if (j == 0 && xb == 0) {
       loss_d += 0.5f * e * e / var * invB;
       if (SIGMA || cfg.slice_variance) loss_s += 0.5f * logf(var) * invB;
@@ -425,12 +481,58 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
       *reinterpret_cast<uint4*>(gt + L::tg + umma::tile_off(srow, 0, 16)) =
           make_uint4((uint32_t)__half_as_ushort(__float2half_rn(g0)), 0u, 0u, 0u);
       *reinterpret_cast<uint4*>(gt + L::tg + umma::tile_off(srow, 8, 16)) = make_uint4(0u, 0u, 0u, 0u);
+      if (BIAS) {
+        *reinterpret_cast<uint4*>(gt + L::tgb + umma::tile_off(srow, 0, 16)) =
+            make_uint4((uint32_t)__half_as_ushort(__float2half_rn(fminf(fmaxf(d_lb * gscale, -65504.f), 65504.f))), 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(gt + L::tgb + umma::tile_off(srow, 8, 16)) = make_uint4(0u, 0u, 0u, 0u);
+      }
     }
     if (wide) cta_barrier_all();  // the partner group has finished reading this group's rho / xw rows
     tick(4);
     publish();
 
     // ================= phase 3: backward on tcgen05 =================
+    if (BIAS) {
+      if (issuer) {
+        umma::fence_after_sync();
+        mma_wgrad(L::c_wbo, s_tbh, s_tgb, RG16, 16);      // dWbo^T += Hb^T Gb
+        mma_dgrad(s_tgb, RG16, s_wbo, RG64, 16, 64);       // dHb = Gb Wbo
+        umma::commit(mbar);
+      }
+      wait_mma();
+      epi_mask_store(td + tlane + 32 * half, gt + L::tbh, erow, 32 * half);
+      publish();
+      if (issuer) {
+        umma::fence_after_sync();
+        mma_wgrad(L::c_wb0, s_tbh, s_tbx, RG32, 32);       // dWb0 += dZb^T [se | pe_bias | 0]
+        mma_dgrad(s_tbh, RG64, s_wb0, RG32, 64, 32);       // d[se | pe_bias | 0] = dZb Wb0
+        umma::commit(mbar);
+      }
+      wait_mma();
+      {
+        uint32_t d[16];
+        umma::tmem_ld16(td + tlane + 16 * half, d);
+        umma::tmem_ld_wait();
+        if (half == 0) {  // d(slice embedding): column sums over the warp's 32 rows (one pixel, one slice)
+          const int64_t pe = (tile * kGR + erow) >> a.log2S;
+          const int ke = (int)a.slice_idx[pe];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const float s = warp_sum(__uint_as_float(d[c]));
+            if (lane == c) red_add(a.g_se + (size_t)ke * 16 + c, s * inv_gscale);
+          }
+        } else {  // columns 16..23: dL/d(pe_bias), parked until the density pass has produced dL/d(features)
+          const int nb = cfg.n_levels_bias;
+          float* pb = reinterpret_cast<float*>(gt + L::dxb) + erow * 8;
+          float g[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) g[c] = (c >> 1) < nb ? __uint_as_float(d[c]) : 0.f;
+          *reinterpret_cast<float4*>(pb) = make_float4(g[0], g[1], g[2], g[3]);
+          *reinterpret_cast<float4*>(pb + 4) = make_float4(g[4], g[5], g[6], g[7]);
+        }
+      }
+      publish();
+    }
     if (SIGMA) {
       if (issuer) {
         umma::fence_after_sync();
@@ -516,11 +618,16 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
     acc_on = 1u;
     // dL/d(features): fp32 [128][32], feature pair (2l, 2l+1) of row r at r*32 + ((2l) ^ ((r & 15) << 1)) -- 8-byte
     // accesses, conflict-free for both the row-per-lane epilogue writes and the sample-pair reads of the scatter
-    float* sdx = reinterpret_cast<float*>(gt + (L::alias_dx ? L::th + (size_t)(DEPTH - 1) * 128 * 64 * 2 : L::dx));
+    float* sdx = reinterpret_cast<float*>(gt + (BIAS ? L::tbh : (L::alias_dx ? L::th + (size_t)(DEPTH - 1) * 128 * 64 * 2 : L::dx)));
     if (!(a.ablate & 4u)) {
       uint32_t d[16];
       umma::tmem_ld16(td + tlane + 16 * half, d);
       umma::tmem_ld_wait();
+      if (BIAS && half == 0) {  // + the bias head's gradient w.r.t. the first 8 encoded features
+        const float* pb = reinterpret_cast<const float*>(gt + L::dxb) + erow * 8;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) d[c] = __float_as_uint(__uint_as_float(d[c]) + pb[c]);
+      }
 #pragma unroll
       for (int c = 0; c < 16; c += 2)
         *reinterpret_cast<float2*>(&sdx[erow * 32 + ((16 * half + c) ^ ((erow & 15) << 1))]) =
@@ -606,6 +713,11 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
       flush(L::c_ws0, 32, gs, 32, false);
       flush(L::c_wso, 16, gs + 64 * 32, 64, true);
     }
+    if (BIAS) {
+      float* gb = a.g_mlp + a.off_bias;
+      flush(L::c_wb0, 32, gb, 32, false);
+      flush(L::c_wbo, 16, gb + 64 * 32, 64, true);
+    }
   }
   loss_d = warp_sum(loss_d);
   loss_s = warp_sum(loss_s);
@@ -620,11 +732,11 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
   if (warp == 0) umma::tmem_dealloc(tm, 512);
 }
 
-template <int DEPTH, bool SIGMA>
+template <int DEPTH, bool SIGMA, bool BIAS = false>
 int launch_tc(const FusedArgs& a, cudaStream_t st) {
-  using L = TcLayout<DEPTH, SIGMA>;
+  using L = TcLayout<DEPTH, SIGMA, BIAS>;
   static_assert(L::bytes <= 227 * 1024, "shared memory");
-  cudaError_t e = cudaFuncSetAttribute(inr_train_tc_kernel<DEPTH, SIGMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
+  cudaError_t e = cudaFuncSetAttribute(inr_train_tc_kernel<DEPTH, SIGMA, false, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
   if (e != cudaSuccess) {
     set_error("nsv_inr_train_step(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return (int)e;
@@ -635,10 +747,11 @@ int launch_tc(const FusedArgs& a, cudaStream_t st) {
     cudaFuncSetAttribute(inr_train_tc_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcLayout<3, false>::bytes);
     inr_train_tc_kernel<3, false, true><<<grid, kThreads, L::bytes, st>>>(a);
   } else {
-    inr_train_tc_kernel<DEPTH, SIGMA><<<grid, kThreads, L::bytes, st>>>(a);
+    inr_train_tc_kernel<DEPTH, SIGMA, false, BIAS><<<grid, kThreads, L::bytes, st>>>(a);
   }
   if (int err = check_launch("nsv_inr_train_step(tcgen05)")) return err;
-  inr_finalize_kernel<<<1, 256, 0, st>>>(a.logit_coef, a.g_c, a.losses, a.n_slices, a.cfg.slice_scale, a.cfg.image_reg, a.cfg.delta);
+  inr_finalize_kernel<<<1, 256, 0, st>>>(a.logit_coef, a.g_c, a.losses, a.n_slices, a.cfg.slice_scale, a.cfg.image_reg, a.cfg.delta,
+                                         a.cfg.n_levels_bias);
   return check_launch("nsv_inr_train_step(finalize)");
 }
 
@@ -650,6 +763,13 @@ int launch_train_tc(const FusedArgs& a, cudaStream_t st) {
   if (c.width != kW || c.depth < 1 || c.depth > 3 || (c.pixel_variance && c.depth != 1) || (a.B * (int64_t)a.S) % (kGR * kNGroups) != 0) {
     set_error("nsv_inr_train_step: no tcgen05 instantiation for width=%d depth=%d (needs width 64, depth 1..3, B*S %% 256 == 0)", c.width, c.depth);
     return NSV_EUNSUPPORTED;
+  }
+  if (c.n_levels_bias) {
+    if (!c.pixel_variance || c.n_levels_bias > 4) {
+      set_error("nsv_inr_train_step: the fused bias-field head needs the sigma_net heads on (pixel variance, depth 1) and n_levels_bias <= 4");
+      return NSV_EUNSUPPORTED;
+    }
+    return launch_tc<1, true, true>(a, st);
   }
   if (c.pixel_variance) return launch_tc<1, true>(a, st);
   if (c.depth == 1) return launch_tc<1, false>(a, st);

@@ -103,7 +103,8 @@ class FusedState:
         sc = model is not None and not a.no_slice_scale
         pg = model is not None and not a.no_transformation_optimization
         if model is not None:
-            _require(a.n_levels_bias == 0, "the bias-field head (n_levels_bias > 0) is not fused yet")
+            _require(a.n_levels_bias == 0 or (pv and 1 <= a.n_levels_bias <= 4 and a.width == 64),
+                     "the fused bias-field head needs 1 <= n_levels_bias <= 4, width 64 and the pixel-variance (sigma_net) heads on")
             _require(not pv or (a.depth == 1 and a.n_features_slice == 16 and a.n_features_z == 15),
                      "fused sigma_net needs depth=1, n_features_slice=16, n_features_z=15")
         self.cfg = make_config(inr, a, delta=(model.delta if model is not None else 0.0), n_batch_samples=n_batch_samples,
@@ -181,6 +182,9 @@ class FusedState:
                 if self.cfg.pixel_variance:
                     s = _pack_sigma(m.sigma_net.params.detach(), self.args.width)
                     mlp[self.off_sigma : self.off_sigma + s.numel()].copy_(s)
+                if self.cfg.n_levels_bias:  # b_net's logical column order [slice embedding | pe_bias | pad] is the packed one
+                    b = m.b_net.params.detach()
+                    mlp[self.off_bias : self.off_bias + b.numel()].copy_(b)
                 for name, t in (("slice_embedding", getattr(getattr(m, "slice_embedding", None), "weight", None)),
                                 ("logit_coef", getattr(m, "logit_coef", None)), ("log_var_slice", getattr(m, "log_var_slice", None)),
                                 ("axisangle", m.axisangle)):
@@ -199,6 +203,9 @@ class FusedState:
                 if self.cfg.pixel_variance:
                     n = m.sigma_net.params.numel()
                     m.sigma_net.params.copy_(_unpack_sigma(mlp[self.off_sigma : self.off_sigma + n], self.args.width))
+                if self.cfg.n_levels_bias:
+                    n = m.b_net.params.numel()
+                    m.b_net.params.copy_(mlp[self.off_bias : self.off_bias + n])
                 for name, t in (("slice_embedding", getattr(getattr(m, "slice_embedding", None), "weight", None)),
                                 ("logit_coef", getattr(m, "logit_coef", None)), ("log_var_slice", getattr(m, "log_var_slice", None)),
                                 ("axisangle", m.axisangle)):
@@ -229,8 +236,11 @@ class FusedState:
         return g
 
     # ------------------------------------------------------------------ one forward+backward
-    def forward_backward(self, xyz, v, slice_idx, noise=None, seed: int = 0, offset: int = 0, want_v_out: bool = False):
-        """Accumulates gradients into `self.grad` (caller zeroes) and returns (losses[8] view, v_out or None)."""
+    def forward_backward(self, xyz, v, slice_idx, noise=None, seed: int = 0, offset: int = 0, want_v_out: bool = False,
+                         dist=None, world: int = 1):
+        """Accumulates gradients into `self.grad` (caller zeroes, losses included) and returns (losses[8] view, v_out or None).
+        With the bias-field head, `nsv_inr_bias_mean` first leaves mean(log_bias) of the batch in losses[4] (biasReg couples
+        all samples, models.py:323); data-parallel callers pass `dist` / `world` so that the mean is the global one."""
         B = xyz.shape[0]
         S = self.args.n_samples
         xyz = xyz.contiguous().float()
@@ -241,6 +251,19 @@ class FusedState:
             assert noise.shape == (B, S, 3)
         v_out = torch.empty(B, dtype=torch.float32, device=xyz.device) if want_v_out else None
         prm, grd = self.params_struct(), self.grads_struct()
+        if self.cfg.n_levels_bias:
+            with torch.cuda.device(self.device):
+                rc = _lib.lib().nsv_inr_bias_mean(
+                    ctypes.byref(self.cfg), ctypes.byref(prm), _lib.ptr(xyz), _lib.ptr(slice_idx), _lib.ptr(noise), ctypes.c_uint64(seed),
+                    ctypes.c_uint64(offset), ctypes.c_void_p(self.losses.data_ptr() + 16), ctypes.c_int64(B), ctypes.c_int(S),
+                    _lib.stream(self.device))
+            if rc == -2:
+                raise FusedUnsupported(_lib.lib().nsv_last_error_string().decode())
+            _lib.check(rc, "nsv_inr_bias_mean")
+            if dist is not None and world > 1:  # equal per-rank batch sizes: the global mean is the mean of the ranks' means
+                m = self.losses[4:5]
+                dist.all_reduce(m)
+                m.div_(world)
         with torch.cuda.device(self.device):
             rc = _lib.lib().nsv_inr_train_step(
                 ctypes.byref(self.cfg), ctypes.byref(prm), ctypes.byref(grd), _lib.ptr(xyz), _lib.ptr(v), _lib.ptr(slice_idx),
@@ -261,6 +284,8 @@ class FusedState:
         if not (a.no_pixel_variance and a.no_slice_variance):
             out[S_LOSS] = losses[1]
             out[DS_LOSS] = losses[0] + losses[1]
+        if a.n_levels_bias:
+            out[B_REG] = losses[2]
         out[I_REG] = losses[3]
         return out
 
@@ -344,7 +369,7 @@ class FusedTrainer:
         n_q = xyz.shape[0] * a.n_samples
         rank = dist.get_rank()
         losses, _ = st.forward_backward(xyz, v, slice_idx, noise, seed=self.seed + 7919 * rank,
-                                        offset=(self.iteration - 1) * n_q)
+                                        offset=(self.iteration - 1) * n_q, dist=dist, world=world)
         out = st.loss_dict(losses.clone())
         if self.pose and a.weight_transformation:
             out[T_REG] = self._trans_reg()  # identical on every rank: the all-reduce mean leaves it unchanged

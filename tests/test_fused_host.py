@@ -1,0 +1,96 @@
+"""CPU tests of the fused path's host side (nesvor_b200/nesvor/fused.py): how a NeSVoR model is packed into the flat
+buffers kernel A reads -- segment order (trainable prefix first), 16-byte alignment, the per-head offsets that
+nsv_inr_mlp_layout reports, sigma_net's re-slotted first layer, b_net (bias-field head, models.py:247-258) -- and that
+parameters survive the round trip flat -> nn.Module.  No compute entry point is called (there is no GPU here)."""
+from argparse import Namespace
+
+import pytest
+import torch
+
+
+def make_args(**kw):
+    a = dict(n_features_per_level=2, log2_hashmap_size=19, level_scale=1.3819, coarsest_resolution=16.0, finest_resolution=0.5,
+             n_levels_bias=0, depth=1, width=64, n_features_z=15, n_features_slice=16, no_transformation_optimization=False,
+             no_slice_scale=False, no_pixel_variance=False, no_slice_variance=False, single_precision=False,
+             weight_transformation=0.1, weight_bias=100.0, image_regularization="edge", weight_image=2.0, delta=0.2,
+             learning_rate=5e-3, gamma=0.33, milestones=[0.5, 0.75, 0.9], n_iter=10, batch_size=64, n_samples=128,
+             dtype=torch.float16, device=torch.device("cpu"), n_levels=None, base_resolution=None, seed=0)
+    a.update(kw)
+    return Namespace(**a)
+
+
+def build_model(args, n_slices=7):
+    import nesvor_b200 as nb
+
+    g = torch.Generator().manual_seed(3)
+    ax = torch.randn(n_slices, 6, generator=g) * 0.1
+    res = torch.tensor([[1.0, 1.0, 3.0]]).repeat(n_slices, 1)
+    bb = torch.tensor([[-30.0, -30.0, -30.0], [30.0, 30.0, 30.0]])
+    return nb.NeSVoR(nb.RigidTransform(ax, True), res, 0.7, bb, args)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(n_levels_bias=4), dict(n_levels_bias=2, no_slice_variance=True),
+                                dict(depth=3, no_pixel_variance=True, no_slice_variance=True, no_transformation_optimization=True)])
+def test_flat_layout_and_round_trip(native_lib, kw):
+    from nesvor_b200.nesvor.fused import FusedState
+
+    args = make_args(**kw)
+    model = build_model(args)
+    st = FusedState(model.inr, args, model)
+    W = args.width
+    per_density = W * 32 + (args.depth - 1) * W * W + 16 * W
+    per_head = W * 32 + (args.depth - 1) * W * W + 16 * W
+    assert st.off_density == 0 and st.off_sigma == per_density
+    assert st.off_bias == per_density + (0 if args.no_pixel_variance else per_head)
+    assert st.seg("mlp").numel() == st.off_bias + (per_head if args.n_levels_bias else 0)
+    # segments: 16-byte aligned, trainable prefix first, frozen tensors behind it
+    for name, sl in st.offsets.items():
+        assert sl.start % 4 == 0, name
+    names = list(st.offsets)
+    assert names[:2] == ["table", "mlp"]
+    if args.no_transformation_optimization:
+        assert st.offsets["axisangle"].start >= st.n_train
+    else:
+        assert st.offsets["axisangle"].stop <= st.n_train
+    assert st.cfg.n_levels_bias == args.n_levels_bias and st.cfg.w_bias == pytest.approx(args.weight_bias)
+    # flat16 is the rounded flat
+    assert torch.equal(st.flat16, st.flat.to(torch.float16))
+    # heads: what the kernel reads is what the modules hold
+    mlp = st.seg("mlp")
+    d = model.inr.density_net.params.detach()
+    assert torch.equal(mlp[: d.numel()], d)
+    if not args.no_pixel_variance:
+        w0 = model.sigma_net.weight_views()[0].detach()  # logical columns: [slice embedding (16) | z1..z15 | pad]
+        p0 = mlp[st.off_sigma : st.off_sigma + W * 32].view(W, 32)
+        assert torch.equal(p0[:, :16], w0[:, :16]) and torch.equal(p0[:, 17:32], w0[:, 16:31])
+        assert (p0[:, 16] == 0).all()  # z0 never reaches sigma_net (models.py:352: z[..., 1:])
+    if args.n_levels_bias:
+        b = model.b_net.params.detach()
+        assert b.numel() == per_head
+        assert torch.equal(mlp[st.off_bias : st.off_bias + per_head], b)
+    # round trip after an "optimiser step" on the flat buffer
+    with torch.no_grad():
+        st.flat[: st.n_train].mul_(1.5)
+    expect = {n: p.detach().clone() for n, p in model.named_parameters()}
+    st.push_to_model()
+    seg_of = {"slice_embedding.weight": "slice_embedding", "logit_coef": "logit_coef", "log_var_slice": "log_var_slice", "axisangle": "axisangle"}
+    for n, p in model.named_parameters():
+        if n in seg_of and (seg_of[n] not in st.offsets or st.offsets[seg_of[n]].start >= st.n_train):
+            assert torch.equal(p, expect[n]), n  # unused by this configuration: stays behind the trainable prefix, untouched
+        elif n == "sigma_net.params":
+            got, ref = p.detach().view(-1)[: W * 32].view(W, 32), expect[n].view(-1)[: W * 32].view(W, 32)
+            assert torch.allclose(got[:, :31], ref[:, :31] * 1.5)
+            assert (got[:, 31] == 0).all()  # the pad column multiplies zeros: dropped by the packed layout
+        elif p.numel():
+            assert torch.allclose(p.detach(), expect[n] * 1.5), n
+    assert set(st.loss_dict(st.losses)) >= ({"MSE", "imageReg"} | ({"biasReg"} if args.n_levels_bias else set()))
+
+
+def test_unsupported_configurations_raise(native_lib):
+    from nesvor_b200.nesvor.fused import FusedState, FusedUnsupported
+
+    model = build_model(make_args())
+    for kw in (dict(n_levels_bias=5), dict(n_levels_bias=4, no_pixel_variance=True), dict(depth=4), dict(width=48),
+               dict(n_features_z=7), dict(depth=2)):
+        with pytest.raises(FusedUnsupported):
+            FusedState(model.inr, make_args(**kw), model)

@@ -99,3 +99,48 @@ def test_fused_and_unfused_renderers_agree(trained):
         rel = float((vf - vu).norm() / vu.norm())
         print("fused vs unfused renderer, no_output_psf =", no_psf, "rel-L2 =", rel)
         assert rel < tol
+
+
+def test_train_with_fused_bias_field_head(native_lib):
+    """BASELINE config-5 heads end to end: stacks multiplied by a smooth synthetic bias field, train() with
+    n_levels_bias = 4 on the fused kernel (b_net + biasReg through nsv_inr_bias_mean).  The data term must fall,
+    biasReg must stay small (its weight is 100), and the trained b_net must flow back into the nn.Module, where the
+    unfused native path evaluates the same small biasReg."""
+    import nesvor_b200 as nb
+    import psnr_phantom as pp
+    from nesvor_b200.data.phantom import simulate_slices
+    from nesvor_b200.nesvor.fused import FusedTrainer
+    from nesvor_b200.nesvor.train import Dataset
+    from nesvor_b200.nesvor.models import NeSVoR
+
+    dev = torch.device("cuda", 0)
+    args = pp.make_args(dev, n_iter=600, batch_size=2048, n_samples=64, n_levels_bias=4, no_loss_sync=True)
+    torch.manual_seed(0)
+    slices, volume, _ = simulate_slices(device=dev, n=48, n_stacks=3, res_r=1.0, res_s=1.0, gap=2.0)
+    for s in slices:  # smooth multiplicative field in slice coordinates, different per stack orientation
+        h, w = s.image.shape[-2:]
+        yy, xx = torch.meshgrid(torch.linspace(-1, 1, h, device=dev), torch.linspace(-1, 1, w, device=dev), indexing="ij")
+        s.image = s.image * torch.exp(0.3 * torch.cos(1.5 * xx + 0.5 * s.stack_idx) * torch.cos(1.1 * yy))
+    dataset = Dataset(slices, args)
+    model = NeSVoR(dataset.transformation, dataset.resolution, dataset.mean, dataset.bounding_box, args)
+    assert hasattr(model, "b_net")
+    trainer = FusedTrainer(model, args)
+    first, last = [], []
+    for i in range(args.n_iter):
+        losses = trainer.step(**dataset.get_batch(args.batch_size, dev))
+        assert "biasReg" in losses
+        if i < 20:
+            first.append({k: float(v) for k, v in losses.items()})
+        if i >= args.n_iter - 20:
+            last.append({k: float(v) for k, v in losses.items()})
+    mean = lambda rows, k: sum(r[k] for r in rows) / len(rows)  # noqa: E731
+    print("MSE+logVar first/last:", mean(first, "MSE+logVar"), mean(last, "MSE+logVar"), "biasReg last:", mean(last, "biasReg"))
+    assert all(torch.isfinite(torch.tensor(list(r.values()))).all() for r in first + last)
+    assert mean(last, "MSE+logVar") < mean(first, "MSE+logVar") - 0.5
+    assert mean(last, "biasReg") < 1e-2
+    # parameters flow back into the nn.Module (b_net included) and the unfused native path agrees on the losses
+    before = model.b_net.params.detach().clone()
+    trainer.sync_to_model()
+    assert not torch.equal(before, model.b_net.params.detach())
+    ref = model(**dataset.get_batch(512, dev))
+    assert torch.isfinite(ref["biasReg"]) and float(ref["biasReg"]) < 5e-2

@@ -51,7 +51,7 @@ def build_pair(args, n_slices=9, extent=60.0, seed=0):
         width=args.width, depth=args.depth, n_levels_bias=args.n_levels_bias, no_transformation_optimization=args.no_transformation_optimization,
         no_slice_scale=args.no_slice_scale, no_pixel_variance=args.no_pixel_variance, no_slice_variance=args.no_slice_variance,
         image_regularization=args.image_regularization, n_samples=args.n_samples, delta=model.delta,
-        weight_transformation=args.weight_transformation, weight_image=args.weight_image, emulate_fp16=(args.dtype == torch.float16),
+        weight_transformation=args.weight_transformation, weight_image=args.weight_image, weight_bias=args.weight_bias, emulate_fp16=(args.dtype == torch.float16),
         mlp_bias=(args.dtype == torch.float32))
     om = io.OracleNeSVoR(cfg, n_slices, ax, res, bb)
     P = om.P
@@ -63,6 +63,8 @@ def build_pair(args, n_slices=9, extent=60.0, seed=0):
     nets = [("density_net", model.inr.density_net)]
     if hasattr(model, "sigma_net"):
         nets.append(("sigma_net", model.sigma_net))
+    if hasattr(model, "b_net"):
+        nets.append(("b_net", model.b_net))
     for prefix, net in nets:
         if args.dtype == torch.float16:
             for i, w in enumerate(net.weight_views()):
@@ -99,6 +101,10 @@ CONFIGS = {
     "default_all_heads": dict(depth=1, n_samples=256, batch_size=32),
     "tv_two_layers": dict(depth=2, image_regularization="TV", no_pixel_variance=True, n_samples=64, batch_size=64),
     "l2_width32": dict(width=32, image_regularization="L2", n_samples=32, batch_size=128, no_slice_variance=True),
+    # BASELINE config 5 heads: bias field (b_net on the 4 coarsest levels) + pixel / slice variance + pose optimisation
+    "cfg5_bias_all_heads": dict(depth=1, n_levels_bias=4, n_samples=256, batch_size=32),
+    "bias_two_levels": dict(depth=1, n_levels_bias=2, n_samples=64, batch_size=64, no_slice_variance=True, image_regularization="TV",
+                            no_transformation_optimization=True, weight_bias=10.0),
 }
 
 
@@ -118,6 +124,8 @@ def test_fused_train_step_parity(native_lib, name, fused_impl):
 
     if fused_impl in ("tcgen05", "ws") and CONFIGS[name].get("width", 64) != 64:
         pytest.skip("tcgen05 paths are instantiated for width 64 (UMMA M = 64 wgrad)")
+    if fused_impl in ("mma", "ws") and CONFIGS[name].get("n_levels_bias", 0):
+        pytest.skip("the bias-field head is instantiated in the tcgen05 all-phases kernel only")
     args = make_args(**CONFIGS[name])
     n_slices = 9
     model, om = build_pair(args, n_slices)
@@ -133,7 +141,7 @@ def test_fused_train_step_parity(native_lib, name, fused_impl):
     print(f"{name} [{fused_impl}]: rel-L2(v_out) = {err:.3e}")
     assert err <= V_OUT_TOL
     got = st.loss_dict(losses.cpu())
-    for k in ("MSE", "logVar", "imageReg"):
+    for k in ("MSE", "logVar", "imageReg", "biasReg"):
         if k in losses_o:
             np.testing.assert_allclose(float(got[k]), float(losses_o[k]), rtol=2e-3, atol=1e-6, err_msg=k)
     # gradients (fp16 backward operands): table, MLP weights, per-slice parameters
@@ -154,6 +162,10 @@ def test_fused_train_step_parity(native_lib, name, fused_impl):
         ws = torch.cat([om.P[f"sigma_net.w{i}"].grad.reshape(-1) for i in range(args.depth + 1)])
         assert rel_l2(gs, ws) < 2e-2
         assert rel_l2(st.seg("slice_embedding", st.grad).cpu(), om.P["slice_embedding"].grad.reshape(-1)) < 2e-2
+    if args.n_levels_bias:
+        n = model.b_net.params.numel()
+        wb = torch.cat([om.P[f"b_net.w{i}"].grad.reshape(-1) for i in range(args.depth + 1)])
+        assert rel_l2(gd[st.off_bias : st.off_bias + n], wb) < 2e-2
     if not args.no_transformation_optimization:
         assert rel_l2(st.seg("axisangle", st.grad).cpu(), om.P["axisangle"].grad.reshape(-1)) < 3e-2
 
@@ -217,10 +229,10 @@ def test_fused_render_parity(native_lib):
 def test_fused_rejects_unsupported(native_lib):
     from nesvor_b200.nesvor.fused import FusedState, FusedUnsupported
 
-    args = make_args(n_levels_bias=4)
     model, _ = build_pair(make_args(), 4)
-    with pytest.raises(FusedUnsupported):
-        FusedState(model.inr, args, model)
+    for kw in (dict(n_levels_bias=5), dict(n_levels_bias=4, no_pixel_variance=True), dict(depth=4)):
+        with pytest.raises(FusedUnsupported):
+            FusedState(model.inr, make_args(**kw), model)
 
 
 @pytest.fixture

@@ -1,4 +1,9 @@
 set -x
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee gpurun_out/r1_pytest_gpu.log
-timeout 900 python bench.py --steps 50 --warmup 5 2>&1 | tail -3 | tee gpurun_out/r1_bench.log
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
+timeout 400 python -m pytest tests/test_gpu_fused.py "tests/test_gpu_e2e.py::test_train_with_fused_bias_field_head" -x -q -s 2>&1 | grep -v "^$" | tail -40 | tee gpurun_out/r1b_bias_tests.log
+timeout 100 python tools/bench_kernel_a.py --cfg 5 --variants 1048576:1 --reps 10 2>&1 | tail -2 | tee gpurun_out/r1b_cfg5_kernel.log
+timeout 100 python tools/bench_kernel_a.py --cfg 3 --variants 1048576:1 --reps 10 2>&1 | tail -2 | tee gpurun_out/r1b_cfg3_kernel.log
+timeout 60 python tools/run_kernel_b.py 2>&1 | tail -2 | tee gpurun_out/r1b_kernelB_times.log
+timeout 150 ncu --set full --clock-control none --import-source on -k regex:"slice_acq|adjoint" -c 4 -f -o gpurun_out/r1b_kernelB python tools/run_kernel_b.py --reps 0 2>&1 | tail -3
+ls -la gpurun_out

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Kernel-A-only timing sweep over the gather/scatter tuning hooks (BASELINE config 2 by default).
 
-    python tools/bench_kernel_a.py [--variants "agg:fast,agg:fast,..."] [--reps 20] [--cfg 2|3]
+    python tools/bench_kernel_a.py [--variants "agg:fast,agg:fast,..."] [--reps 20] [--cfg 2|3|5]
 
 Prints one line per variant: mean / min kernel time (CUDA events, L2 flushed between launches)."""
 import argparse
@@ -39,12 +39,18 @@ def main():
     if a.cfg == 2:
         args = bench.make_args(dev)
         n, n_stacks, kw = 128, 3, {}
+    elif a.cfg == 5:  # config-5 heads: defaults + bias field on 4 levels (b_net), finest resolution 0.5; 9 stacks x 30 slices at 0.8 mm
+        args = bench.make_args(dev, depth=1, no_pixel_variance=False, no_slice_variance=False, no_transformation_optimization=False,
+                               n_levels=None, n_samples=256, batch_size=4096, n_levels_bias=4, finest_resolution=0.5)
+        n, n_stacks, kw = 138, 9, dict(res_r=0.8, res_s=0.8, n_slice=30)
     else:  # config-3 heads: defaults (depth 1, sigma_net, slice variance, pose optimisation), S = 256
         args = bench.make_args(dev, depth=1, no_pixel_variance=False, no_slice_variance=False, no_transformation_optimization=False,
                                n_levels=None, n_samples=256, batch_size=4096)
         n, n_stacks, kw = 128, 3, dict(motion_deg=3.0, motion_mm=1.5)
     torch.manual_seed(0)
-    slices, _, _ = simulate_slices(n=n, n_stacks=n_stacks, res_r=1.0, res_s=1.0, gap=3.0, device=dev, **kw)
+    sim = dict(res_r=1.0, res_s=1.0, gap=3.0)
+    sim.update(kw)
+    slices, _, _ = simulate_slices(n=n, n_stacks=n_stacks, device=dev, **sim)
     dataset = Dataset(slices, args)
     model = nb.NeSVoR(dataset.transformation, dataset.resolution, dataset.mean, dataset.bounding_box, args)
     trainer = FusedTrainer(model, args)

@@ -62,7 +62,7 @@ def oracle_from_model(model, args, n_slices, resolution, emulate_fp16=False):
         width=args.width, depth=args.depth, n_levels_bias=args.n_levels_bias, no_transformation_optimization=args.no_transformation_optimization,
         no_slice_scale=args.no_slice_scale, no_pixel_variance=args.no_pixel_variance, no_slice_variance=args.no_slice_variance,
         image_regularization=args.image_regularization, n_samples=args.n_samples, delta=model.delta,
-        weight_transformation=args.weight_transformation, weight_image=args.weight_image, emulate_fp16=emulate_fp16, mlp_bias=False)
+        weight_transformation=args.weight_transformation, weight_image=args.weight_image, weight_bias=args.weight_bias, emulate_fp16=emulate_fp16, mlp_bias=False)
     ax = model.axisangle.detach().cpu().float()
     om = io.OracleNeSVoR(cfg, n_slices, ax, resolution.detach().cpu().float(), model.inr.bounding_box.detach().cpu().float())
     P = om.P
@@ -74,6 +74,8 @@ def oracle_from_model(model, args, n_slices, resolution, emulate_fp16=False):
     nets = [("density_net", model.inr.density_net)]
     if hasattr(model, "sigma_net"):
         nets.append(("sigma_net", model.sigma_net))
+    if hasattr(model, "b_net"):
+        nets.append(("b_net", model.b_net))
     for prefix, net in nets:
         for i, w in enumerate(net.weight_views()):
             put(f"{prefix}.w{i}", w)
