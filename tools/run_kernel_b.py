@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Runs the slice-acquisition family (kernel B) once per operator on the BASELINE config-2 stacks -- the target of
-`ncu --set full -k regex:slice_acq|adjoint` captures (profiles/) -- and prints CUDA-event timings per operator.
+`ncu --set full -k regex:"forward_kernel|backward_kernel"` captures (profiles/) -- and prints CUDA-event timings per operator.
 
     python tools/run_kernel_b.py [--reps 5]
 """
@@ -48,7 +48,7 @@ def main():
             torch.cuda.synchronize()
             if i >= 1:
                 durs.append(k0.elapsed_time(k1))
-        return out, sum(durs) / len(durs)
+        return out, (sum(durs) / len(durs) if durs else float('nan'))
 
     slices, t_fwd = timed(lambda: slice_acquisition(mat, vol, None, None, psf, (ss, ss), 1.0, False, False))
     n_px = slices.numel()
