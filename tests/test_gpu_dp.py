@@ -21,3 +21,15 @@ def test_peer_memory_optimizer_matches_allreduce(native_lib):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0
+
+
+def test_bias_field_head_data_parallel(native_lib):
+    """Config-5 heads over 2 ranks: the global mean(log_bias) (biasReg) and the rank-averaged gradient must equal one
+    launch over the concatenated batch (tools/dp_bias_check.py)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", os.path.join(ROOT, "tools", "dp_bias_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:], r.stderr[-2000:])
+    assert r.returncode == 0
