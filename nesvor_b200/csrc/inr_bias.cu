@@ -6,8 +6,9 @@
 // the sample positions (same noise: caller tensor or Philox(seed, offset + sample index)), the first
 // n_levels_bias <= 4 hash-grid levels (all dense and a few thousand entries: L1-resident), the slice embedding,
 // and the 24 -> 64 -> 1 ReLU MLP with kernel A's rounding points (fp16 inputs / weights / hidden activations, fp32
-// accumulation).  Thread = sample on the CUDA cores: 1.6 kFLOP per sample is ~5 % of kernel A's time and needs none
-// of its tile machinery.  The result is added to *out_mean (= losses[4] of nsv_inr_grads), which the caller may
+// accumulation).  Thread = sample on the CUDA cores; the slice-embedding part of the first layer (16 of the 24 inputs)
+// is shared by all samples of a pixel and computed once per pixel in shared memory, which leaves ~0.6 kFLOP per
+// sample -- a few percent of kernel A's time, with none of its tile machinery.  The result is added to *out_mean (= losses[4] of nsv_inr_grads), which the caller may
 // all-reduce over data-parallel ranks before nsv_inr_train_step consumes it.
 #include "inr_common.cuh"
 
@@ -21,6 +22,7 @@ __global__ void __launch_bounds__(kBiasThreads) inr_bias_mean_kernel(const __gri
   __shared__ __align__(16) float w0[kW64 * kBiasIn];  // first layer, fp16 values widened once: [64][24]
   __shared__ float wo[kW64];                          // row 0 of the [16][64] output layer
   __shared__ float red[kBiasThreads / 32];
+  __shared__ float pse[8 * kW64];                     // slice-embedding part of the pre-activations, per pixel of the block's chunk
   const nsv_inr_config& cfg = a.cfg;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const __half* wb = a.mlp + a.off_bias;
@@ -30,8 +32,27 @@ __global__ void __launch_bounds__(kBiasThreads) inr_bias_mean_kernel(const __gri
   const int nb = cfg.n_levels_bias;
   const int64_t N = a.B * (int64_t)a.S;
   float acc = 0.f;
-  for (int64_t sidx = (int64_t)blockIdx.x * kBiasThreads + tid; sidx < N; sidx += (int64_t)gridDim.x * kBiasThreads) {
+  // a block walks chunks of 256 consecutive samples = 256 / S whole pixels (or part of one): the 16 slice-embedding
+  // inputs are shared by all samples of a pixel, so their 64 partial pre-activations are computed once per pixel
+  const int npix = a.S >= kBiasThreads ? 1 : kBiasThreads >> a.log2S;
+  for (int64_t base = (int64_t)blockIdx.x * kBiasThreads; base < N; base += (int64_t)gridDim.x * kBiasThreads) {
+    const int64_t p0 = base >> a.log2S;
+    __syncthreads();  // the previous chunk's readers of pse are done
+    for (int i = tid; i < npix * kW64; i += kBiasThreads) {
+      const int pix = i / kW64, j = i % kW64;
+      float s = 0.f;
+      if (p0 + pix < a.B) {
+        const float* se = a.slice_embedding + (size_t)a.slice_idx[p0 + pix] * 16;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) s = fmaf(w0[j * kBiasIn + c], __half2float(__float2half_rn(__ldg(se + c))), s);
+      }
+      pse[i] = s;
+    }
+    __syncthreads();
+    const int64_t sidx = base + tid;
+    if (sidx >= N) continue;
     const int64_t p = sidx >> a.log2S;
+    const float* ps = pse + (int)(p - p0) * kW64;
     const int k = (int)a.slice_idx[p];
     // ---- sample position: identical arithmetic to kernel A's phase 0 ----
     float ax[6], R[9], y[3], xn[3];
@@ -55,18 +76,7 @@ __global__ void __launch_bounds__(kBiasThreads) inr_bias_mean_kernel(const __gri
       }
     }
     // ---- b_net input [slice embedding (16) | pe_bias (8)], rounded to fp16 like kernel A's operand tile ----
-    float x[kBiasIn];
-    {
-      const float4* se = reinterpret_cast<const float4*>(a.slice_embedding + (size_t)k * 16);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 v = __ldg(se + i);
-        x[4 * i] = __half2float(__float2half_rn(v.x));
-        x[4 * i + 1] = __half2float(__float2half_rn(v.y));
-        x[4 * i + 2] = __half2float(__float2half_rn(v.z));
-        x[4 * i + 3] = __half2float(__float2half_rn(v.w));
-      }
-    }
+    float x[8];
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
       float f0 = 0.f, f1 = 0.f;
@@ -99,17 +109,17 @@ __global__ void __launch_bounds__(kBiasThreads) inr_bias_mean_kernel(const __gri
         f0 = hf.x;
         f1 = hf.y;
       }
-      x[16 + 2 * l] = f0;
-      x[17 + 2 * l] = f1;
+      x[2 * l] = f0;
+      x[2 * l + 1] = f1;
     }
     // ---- 24 -> 64 (ReLU, fp16 activations) -> 1 ----
     float lb = 0.f;
 #pragma unroll 4
     for (int j = 0; j < kW64; ++j) {
-      const float4* wr = reinterpret_cast<const float4*>(w0 + j * kBiasIn);
-      float s = 0.f;
+      const float4* wr = reinterpret_cast<const float4*>(w0 + j * kBiasIn + 16);
+      float s = ps[j];
 #pragma unroll
-      for (int c = 0; c < kBiasIn / 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         const float4 wv = wr[c];
         s = fmaf(wv.x, x[4 * c], s);
         s = fmaf(wv.y, x[4 * c + 1], s);

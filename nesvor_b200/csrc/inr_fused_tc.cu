@@ -68,7 +68,8 @@ struct TcLayout {
   static constexpr uint32_t c_wb0 = c_wso + 16;                           // dWb0  [64 x 32]
   static constexpr uint32_t c_wbo = c_wb0 + 32;                           // dWbo^T [64 x 16]
   static constexpr uint32_t c_end = c_wbo + 16;
-  static_assert(c_end <= 512, "TMEM columns");
+  static constexpr uint32_t c_d2 = 384;                                   // BIAS: b_net's forward / dgrad region, group g: [384 + 64 g, +64)
+  static_assert(c_end <= (BIAS ? c_d2 : 512), "TMEM columns");
 };
 
 __device__ __forceinline__ void cta_barrier_all() { asm volatile("bar.sync 3, 512;" ::: "memory"); }
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
   umma::fence_after_sync();
   const uint32_t tm = *tmem_slot;
   const uint32_t td = tm + L::c_d + 64u * grp;                       // this group's forward / dgrad region
+  const uint32_t td2 = tm + L::c_d2 + 64u * grp;                     // BIAS: second region, so that b_net's products ride in the same MMA rounds
   const uint32_t tacc = tm + ((16u * grp) << 16);                    // this group's wgrad accumulators (lane offset)
   const uint32_t tlane = (uint32_t)(32 * q4) << 16;                  // epilogue lane quarter
   const bool issuer = (gw == 0 && lane == 0);
@@ -203,17 +205,19 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
   const float bias_mean = BIAS ? __ldg(a.losses + 4) : 0.f;
   constexpr uint32_t RG64 = 8 * 128, RG32 = 4 * 128, RG16 = 2 * 128;  // byte stride between 8-row groups of a tile
   // forward: D[128 x N] = A[128 x K] W[N x K]^T  (A, W K-major)
-  auto mma_fwd = [&](uint32_t s_a, uint32_t rg_a, uint32_t s_w, uint32_t rg_w, int K, int N) {
+  auto mma_fwd_d = [&](uint32_t d, uint32_t s_a, uint32_t rg_a, uint32_t s_w, uint32_t rg_w, int K, int N) {
     for (int k = 0; k < K / 16; ++k)
-      umma::mma_f16(td, umma::smem_desc(s_a + k * 256, 128, rg_a), umma::smem_desc(s_w + k * 256, 128, rg_w),
+      umma::mma_f16(d, umma::smem_desc(s_a + k * 256, 128, rg_a), umma::smem_desc(s_w + k * 256, 128, rg_w),
                     umma::instr_desc(128, N, false, false), k > 0);
   };
+  auto mma_fwd = [&](uint32_t s_a, uint32_t rg_a, uint32_t s_w, uint32_t rg_w, int K, int N) { mma_fwd_d(td, s_a, rg_a, s_w, rg_w, K, N); };
   // dgrad: D[128 x N] = dC[128 x K] W[K x N]  (W tile as MN-major B)
-  auto mma_dgrad = [&](uint32_t s_dc, uint32_t rg_dc, uint32_t s_w, uint32_t rg_w, int K, int N) {
+  auto mma_dgrad_d = [&](uint32_t d, uint32_t s_dc, uint32_t rg_dc, uint32_t s_w, uint32_t rg_w, int K, int N) {
     for (int k = 0; k < K / 16; ++k)
-      umma::mma_f16(td, umma::smem_desc(s_dc + k * 256, 128, rg_dc), umma::smem_desc(s_w + k * 2 * rg_w, rg_w, 128),
+      umma::mma_f16(d, umma::smem_desc(s_dc + k * 256, 128, rg_dc), umma::smem_desc(s_w + k * 2 * rg_w, rg_w, 128),
                     umma::instr_desc(128, N, false, true), k > 0);
   };
+  auto mma_dgrad = [&](uint32_t s_dc, uint32_t rg_dc, uint32_t s_w, uint32_t rg_w, int K, int N) { mma_dgrad_d(td, s_dc, rg_dc, s_w, rg_w, K, N); };
   // wgrad: acc[64 x N] += P[128 x 64]^T Q[128 x N]  (both tiles MN-major, K = the 128 sample rows)
   auto mma_wgrad = [&](uint32_t col, uint32_t s_p, uint32_t s_q, uint32_t rg_q, int N) {
     for (int k = 0; k < kGR / 16; ++k)
@@ -274,17 +278,45 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
     const bool slow = encode_warp(xn, lt, cfg.grid.n_levels, a.table,
                 [&](int l, __half2 v) { *reinterpret_cast<__half2*>(gt + L::tx + umma::tile_off(srow, 2 * l, 32)) = v; },
                 [&](int c, uint4 v) { *reinterpret_cast<uint4*>(gt + L::tx + umma::tile_off(srow, 8 * c, 32)) = v; });
+    if (BIAS) {
+      // b_net's input [slice embedding (16) | pe_bias (2 n_levels_bias) | 0] (models.py:344-347) depends on nothing the MLPs
+      // produce: the gather lanes build it here (each lane of a pair converts 8 of the 16 embedding values, which also
+      // serve sigma_net's input tile), so that b_net's products share the density / sigma MMA rounds
+      const float4* se = reinterpret_cast<const float4*>(a.slice_embedding + (size_t)k * 16 + 8 * xb);
+      const float4 s0 = __ldg(se), s1 = __ldg(se + 1);
+      uint4 v;
+      {
+        const __half2 h0 = __floats2half2_rn(s0.x, s0.y), h1 = __floats2half2_rn(s0.z, s0.w);
+        const __half2 h2 = __floats2half2_rn(s1.x, s1.y), h3 = __floats2half2_rn(s1.z, s1.w);
+        v = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                       *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+      }
+      *reinterpret_cast<uint4*>(gt + L::tsx + umma::tile_off(srow, 8 * xb, 32)) = v;
+      *reinterpret_cast<uint4*>(gt + L::tbx + umma::tile_off(srow, 8 * xb, 32)) = v;
+      __syncwarp();
+      uint4 f = make_uint4(0u, 0u, 0u, 0u);
+      if (xb == 0) {  // features of levels 0..3 of this row (stored by this lane above), masked to the first n_levels_bias
+        f = *reinterpret_cast<const uint4*>(gt + L::tx + umma::tile_off(srow, 0, 32));
+        const int nb = cfg.n_levels_bias;
+        if (nb < 2) f.y = 0u;
+        if (nb < 3) f.z = 0u;
+        if (nb < 4) f.w = 0u;
+      }
+      *reinterpret_cast<uint4*>(gt + L::tbx + umma::tile_off(srow, 16 + 8 * xb, 32)) = f;
+    }
     tick(0);
     publish();
     if (!(a.ablate & 4u)) {
-    // ================= phase 1: density MLP forward on tcgen05 =================
+    // ================= phase 1: density MLP forward on tcgen05 (+ b_net, same rounds, second TMEM region) =================
     if (issuer) {
       umma::fence_after_sync();
       mma_fwd(s_tx, RG32, s_w0, RG32, 32, 64);
+      if (BIAS) mma_fwd_d(td2, s_tbx, RG32, s_wb0, RG32, 32, 64);
       umma::commit(mbar);
     }
     wait_mma();
     epi_relu_store(td + tlane + 32 * half, gt + L::th, erow, 32 * half);
+    if (BIAS) epi_relu_store(td2 + tlane + 32 * half, gt + L::tbh, erow, 32 * half);
 #pragma unroll
     for (int l = 1; l < DEPTH; ++l) {
       publish();
@@ -300,6 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
     if (issuer) {
       umma::fence_after_sync();
       mma_fwd(s_th + (DEPTH - 1) * 128 * 64 * 2, RG64, s_wo, RG64, 64, 16);
+      if (BIAS) mma_fwd_d(td2, s_tbh, RG64, s_wbo, RG64, 64, 16);
       umma::commit(mbar);
     }
     wait_mma();
@@ -321,16 +354,12 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
           *reinterpret_cast<uint4*>(gt + L::tsx + umma::tile_off(erow, 16 + 8 * i, 32)) = v;
         }
       }
-      if (BIAS) {  // b_net input columns 16..23 = features of the first n_levels_bias levels (models.py:344-347), 24..31 = 0
-        uint4 f = *reinterpret_cast<const uint4*>(gt + L::tx + umma::tile_off(erow, 0, 32));
-        const int nb = cfg.n_levels_bias;
-        if (nb < 2) f.y = 0u;
-        if (nb < 3) f.z = 0u;
-        if (nb < 4) f.w = 0u;
-        *reinterpret_cast<uint4*>(gt + L::tbx + umma::tile_off(erow, 16, 32)) = f;
-        *reinterpret_cast<uint4*>(gt + L::tbx + umma::tile_off(erow, 24, 32)) = make_uint4(0u, 0u, 0u, 0u);
-      }
-    } else if (SIGMA) {  // sigma_net (and b_net) input columns 0..15 = slice embedding of the row's slice
+    } else if (BIAS) {  // log_bias of row erow (the slice-embedding columns were written in phase 0)
+      uint32_t zb[16];
+      umma::tmem_ld16(td2 + tlane, zb);
+      umma::tmem_ld_wait();
+      sf[L::flb + grp * kGR + erow] = __uint_as_float(zb[0]);
+    } else if (SIGMA) {  // sigma_net input columns 0..15 = slice embedding of the row's slice
       const int64_t pe = (tile * kGR + erow) >> a.log2S;
       const float* se = a.slice_embedding + (size_t)a.slice_idx[pe] * 16;
 #pragma unroll
@@ -343,7 +372,6 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
           pv[q] = *reinterpret_cast<const uint32_t*>(&h);
         }
         *reinterpret_cast<uint4*>(gt + L::tsx + umma::tile_off(erow, 8 * i, 32)) = v;
-        if (BIAS) *reinterpret_cast<uint4*>(gt + L::tbx + umma::tile_off(erow, 8 * i, 32)) = v;
       }
     }
     // ================= phase 1b: sigma MLP forward =================
@@ -368,30 +396,6 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
         umma::tmem_ld16(td + tlane, z);
         umma::tmem_ld_wait();
         sf[L::flv + grp * kGR + erow] = __uint_as_float(z[0]);
-      }
-    }
-    // ================= phase 1c: bias-field MLP forward (b_net, models.py:247-258,344-347) =================
-    if (BIAS) {
-      publish();
-      if (issuer) {
-        umma::fence_after_sync();
-        mma_fwd(s_tbx, RG32, s_wb0, RG32, 32, 64);
-        umma::commit(mbar);
-      }
-      wait_mma();
-      epi_relu_store(td + tlane + 32 * half, gt + L::tbh, erow, 32 * half);
-      publish();
-      if (issuer) {
-        umma::fence_after_sync();
-        mma_fwd(s_tbh, RG64, s_wbo, RG64, 64, 16);
-        umma::commit(mbar);
-      }
-      wait_mma();
-      if (half == 0) {
-        uint32_t z[16];
-        umma::tmem_ld16(td + tlane, z);
-        umma::tmem_ld_wait();
-        sf[L::flb + grp * kGR + erow] = __uint_as_float(z[0]);
       }
     }
     tick(3);
@@ -491,78 +495,57 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
     tick(4);
     publish();
 
-    // ================= phase 3: backward on tcgen05 =================
-    if (BIAS) {
-      if (issuer) {
-        umma::fence_after_sync();
-        mma_wgrad(L::c_wbo, s_tbh, s_tgb, RG16, 16);      // dWbo^T += Hb^T Gb
-        mma_dgrad(s_tgb, RG16, s_wbo, RG64, 16, 64);       // dHb = Gb Wbo
-        umma::commit(mbar);
-      }
-      wait_mma();
-      epi_mask_store(td + tlane + 32 * half, gt + L::tbh, erow, 32 * half);
-      publish();
-      if (issuer) {
-        umma::fence_after_sync();
-        mma_wgrad(L::c_wb0, s_tbh, s_tbx, RG32, 32);       // dWb0 += dZb^T [se | pe_bias | 0]
-        mma_dgrad(s_tbh, RG64, s_wb0, RG32, 64, 32);       // d[se | pe_bias | 0] = dZb Wb0
-        umma::commit(mbar);
-      }
-      wait_mma();
-      {
-        uint32_t d[16];
-        umma::tmem_ld16(td + tlane + 16 * half, d);
-        umma::tmem_ld_wait();
-        if (half == 0) {  // d(slice embedding): column sums over the warp's 32 rows (one pixel, one slice)
-          const int64_t pe = (tile * kGR + erow) >> a.log2S;
-          const int ke = (int)a.slice_idx[pe];
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const float s = warp_sum(__uint_as_float(d[c]));
-            if (lane == c) red_add(a.g_se + (size_t)ke * 16 + c, s * inv_gscale);
-          }
-        } else {  // columns 16..23: dL/d(pe_bias), parked until the density pass has produced dL/d(features)
-          const int nb = cfg.n_levels_bias;
-          float* pb = reinterpret_cast<float*>(gt + L::dxb) + erow * 8;
-          float g[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) g[c] = (c >> 1) < nb ? __uint_as_float(d[c]) : 0.f;
-          *reinterpret_cast<float4*>(pb) = make_float4(g[0], g[1], g[2], g[3]);
-          *reinterpret_cast<float4*>(pb + 4) = make_float4(g[4], g[5], g[6], g[7]);
-        }
-      }
-      publish();
-    }
+    // ================= phase 3: backward on tcgen05 (b_net rides in the sigma rounds, second TMEM region) =================
     if (SIGMA) {
       if (issuer) {
         umma::fence_after_sync();
         mma_wgrad(L::c_wso, s_tsh, s_tg, RG16, 16);       // dWso^T += Hs^T G
         mma_dgrad(s_tg, RG16, s_wso, RG64, 16, 64);        // dHs = G Wso
+        if (BIAS) {
+          mma_wgrad(L::c_wbo, s_tbh, s_tgb, RG16, 16);            // dWbo^T += Hb^T Gb
+          mma_dgrad_d(td2, s_tgb, RG16, s_wbo, RG64, 16, 64);     // dHb = Gb Wbo
+        }
         umma::commit(mbar);
       }
       wait_mma();
       epi_mask_store(td + tlane + 32 * half, gt + L::tsh, erow, 32 * half);
+      if (BIAS) epi_mask_store(td2 + tlane + 32 * half, gt + L::tbh, erow, 32 * half);
       publish();
       if (issuer) {
         umma::fence_after_sync();
         mma_wgrad(L::c_ws0, s_tsh, s_tsx, RG32, 32);       // dWs0 += dZs^T [se | z]
         mma_dgrad(s_tsh, RG64, s_ws0, RG32, 64, 32);       // d[se | z] = dZs Ws0
+        if (BIAS) {
+          mma_wgrad(L::c_wb0, s_tbh, s_tbx, RG32, 32);            // dWb0 += dZb^T [se | pe_bias | 0]
+          mma_dgrad_d(td2, s_tbh, RG64, s_wb0, RG32, 64, 32);     // d[se | pe_bias | 0] = dZb Wb0
+        }
         umma::commit(mbar);
       }
       wait_mma();
       {
         uint32_t d[16];
         umma::tmem_ld16(td + tlane + 16 * half, d);
+        uint32_t db[16] = {};
+        if (BIAS) umma::tmem_ld16(td2 + tlane + 16 * half, db);
         umma::tmem_ld_wait();
-        if (half == 0) {  // d(slice embedding): column sums over the warp's 32 rows (one pixel, one slice)
+        if (half == 0) {  // d(slice embedding): column sums over the warp's 32 rows (one pixel, one slice), both heads
           const int64_t pe = (tile * kGR + erow) >> a.log2S;
           const int ke = (int)a.slice_idx[pe];
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
-            const float s = warp_sum(__uint_as_float(d[c]));
+            const float s = warp_sum(__uint_as_float(d[c]) + (BIAS ? __uint_as_float(db[c]) : 0.f));
             if (lane == c) red_add(a.g_se + (size_t)ke * 16 + c, s * inv_gscale);
           }
-        } else {  // dL/dz from sigma_net (+ dz0 of the render path in column 0) -> the density pass's G tile
+        } else {
+          if (BIAS) {  // b_net columns 16..23: dL/d(pe_bias), parked until the density pass has produced dL/d(features)
+            const int nb = cfg.n_levels_bias;
+            float* pb = reinterpret_cast<float*>(gt + L::dxb) + erow * 8;
+            float gb[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) gb[c] = (c >> 1) < nb ? __uint_as_float(db[c]) : 0.f;
+            *reinterpret_cast<float4*>(pb) = make_float4(gb[0], gb[1], gb[2], gb[3]);
+            *reinterpret_cast<float4*>(pb + 4) = make_float4(gb[4], gb[5], gb[6], gb[7]);
+          }  // dL/dz from sigma_net (+ dz0 of the render path in column 0) -> the density pass's G tile
           float g[16];
 #pragma unroll
           for (int c = 0; c < 16; ++c) g[c] = __uint_as_float(d[c]);

@@ -287,3 +287,64 @@ def test_fused_out_of_box_samples(native_lib, fast, fused_tuning):
     print(f"out-of-box [fast={fast}]: rel-L2(v_out) = {err:.3e}")
     assert err <= V_OUT_TOL
     assert rel_l2(st.seg("table", st.grad).cpu(), om.P["table"].grad) < 2e-2
+
+
+def test_fused_full_size_properties(native_lib):
+    """BASELINE config 2 at its full per-iteration size (8192 px x 128 samples = 2^20 queries, 16 levels, T = 2^19,
+    64 x 3 hidden): the oracle cannot run 2^20 queries in seconds, so parity is checked through size-independent
+    properties plus the oracle on a random subset of the batch's pixels:
+      (1) rendered pixels of 64 random pixels of the full launch == oracle on exactly those pixels (1e-4, north star);
+      (2) the training kernel's forward == the forward-only renderer kernel on the same points and noise (two
+          independently written kernels; slice scale off so that v_out is the plain PSF mean);
+      (3) in-kernel Philox noise: same (seed, offset) -> bit-identical v_out, different offset -> different;
+      (4) with the variance heads off the loss gradient is affine in the target intensities v:
+          g(v_a) + g(v_b) = 2 g((v_a + v_b) / 2) up to the fp16 rounding of the backward operands."""
+    from nesvor_b200.nesvor.fused import FusedState, attach_render_state, fused_render
+    import nesvor_b200 as nb
+    from oracle import inr_oracle as io
+
+    args = make_args(depth=3, n_levels=16, base_resolution=9, no_pixel_variance=True, no_slice_variance=True, no_slice_scale=True,
+                     no_transformation_optimization=True, n_samples=128, batch_size=8192)
+    n_slices = 9
+    model, om = build_pair(args, n_slices)
+    xyz, v, idx, noise = make_batch(args, n_slices)
+    B, S = args.batch_size, args.n_samples
+    st = FusedState(model.inr, args, model, n_batch_samples=B * S)
+    dx, dv, di, dn = xyz.cuda(), v.cuda(), idx.cuda(), noise.cuda()
+
+    def run(vv, nz=dn, seed=0, offset=0):
+        st.grad.zero_()
+        losses, v_out = st.forward_backward(dx, vv, di, nz, seed=seed, offset=offset, want_v_out=True)
+        torch.cuda.synchronize()
+        return losses.clone(), v_out, st.grad[: st.n_train].clone()
+
+    l0, v0, g0 = run(dv)
+    assert torch.isfinite(v0).all() and torch.isfinite(g0).all()
+    # (1) oracle on a subset of the pixels of the full launch
+    sel = torch.randperm(B, generator=torch.Generator().manual_seed(3))[:64]
+    _, aux = om.forward(xyz[sel], v[sel], idx[sel], noise[sel], return_aux=True)
+    err = rel_l2(v0.cpu()[sel], aux["v_out"].detach())
+    print(f"full size: rel-L2(v_out[64 of {B}]) vs oracle = {err:.3e}")
+    assert err <= V_OUT_TOL
+    # (2) train-kernel forward vs renderer kernel
+    rs = attach_render_state(model.inr, args)
+    ax = model.axisangle.detach()[di]
+    sig = model.psf_sigma[di]
+    ren = fused_render(model.inr, dx, nb.RigidTransform(ax, True), sig, S, noise=dn, state=rs)
+    err = rel_l2(ren, v0)
+    print(f"full size: train-kernel forward vs renderer kernel rel-L2 = {err:.3e}")
+    assert err <= 1e-5
+    # (3) Philox determinism
+    _, p0, _ = run(dv, nz=None, seed=5, offset=12345)
+    _, p1, _ = run(dv, nz=None, seed=5, offset=12345)
+    _, p2, _ = run(dv, nz=None, seed=5, offset=12345 + B * S)
+    assert torch.equal(p0, p1) and not torch.equal(p0, p2)
+    assert rel_l2(p0, v0) < 0.2  # same estimator, different noise draw
+    # (4) affine in v
+    vb = torch.rand(B, generator=torch.Generator().manual_seed(9)).cuda()
+    _, _, ga = run(dv)
+    _, _, gb = run(vb)
+    _, _, gm = run(0.5 * (dv + vb))
+    lin = float((ga + gb - 2 * gm).norm() / (ga.norm() + gb.norm()))
+    print(f"full size: affinity defect of the gradient in v = {lin:.3e}")
+    assert lin < 5e-3

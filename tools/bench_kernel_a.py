@@ -80,6 +80,25 @@ def main():
         print(json.dumps({"cfg": a.cfg, "impl": a.impl, "agg_max": agg, "fast": fast, "ablate": int(ablate), "ms_mean": sum(durs) / len(durs), "ms_min": min(durs),
                           "gq_per_s": B * S / (min(durs) * 1e-3) / 1e9}), flush=True)
     _lib.set_fused_tuning(-1, -1)
+    if args.n_levels_bias:  # the mean(log_bias) pre-pass alone (part of every forward_backward timed above)
+        import ctypes
+
+        prm = st.params_struct()
+        durs = []
+        for i in range(3 + a.reps):
+            flush.zero_()
+            st.losses.zero_()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record(stream)
+            rc = _lib.lib().nsv_inr_bias_mean(ctypes.byref(st.cfg), ctypes.byref(prm), _lib.ptr(batch["xyz"]), _lib.ptr(batch["slice_idx"]),
+                                              ctypes.c_void_p(0), ctypes.c_uint64(0), ctypes.c_uint64(i * B * S),
+                                              ctypes.c_void_p(st.losses.data_ptr() + 16), ctypes.c_int64(B), ctypes.c_int(S), _lib.stream(dev))
+            k1.record(stream)
+            torch.cuda.synchronize()
+            _lib.check(rc, "nsv_inr_bias_mean")
+            if i >= 3:
+                durs.append(k0.elapsed_time(k1))
+        print(json.dumps({"cfg": a.cfg, "kernel": "nsv_inr_bias_mean", "ms_mean": sum(durs) / len(durs), "ms_min": min(durs)}), flush=True)
     if a.timers:
         import ctypes
 
