@@ -246,11 +246,15 @@ int nsv_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
  * and `peer_param_f16` are HOST arrays of `world` device pointers to every rank's gradient / fp16 parameter buffer
  * (symmetric allocations, peer access enabled); rank `rank` updates the shard given by nsv_adamw_shard_bounds of
  * param / exp_avg / exp_avg_sq (full-size local buffers) and stores the refreshed fp16 values into every rank's copy.
+ * Elements [f32_lo, n) -- the per-slice parameters (slice embedding, slice scale / variance, poses), which the training
+ * kernel reads in fp32 -- are additionally mirrored in fp32 into every rank's `peer_param_f32[r]` (element e at index
+ * e - f32_lo), because only the owner's fp32 master is current.
  * The caller synchronises the ranks before (gradients complete) and after (copies written) and clears its gradient. */
 int nsv_adamw_shard_bounds(int64_t n, int world, int rank, int64_t* lo, int64_t* hi);
 int nsv_adamw_step_dp(float* param, const void* const* peer_grads, float* exp_avg, float* exp_avg_sq,
                       void* const* peer_param_f16, int world, int rank, int64_t n, float lr, float beta1, float beta2,
-                      float eps, float weight_decay, int step, float grad_unscale, void* stream);
+                      float eps, float weight_decay, int step, float grad_unscale,
+                      int64_t f32_lo /* multiple of 4 */, void* const* peer_param_f32 /* or NULL */, void* stream);
 
 /* tcgen05 / TMEM bring-up check used by tests/test_gpu_umma.py: runs every tensor-core operand
  * configuration kernel A uses on fixed 128x64 / 64x64 / 128x16 fp16 inputs (no reference counterpart). */

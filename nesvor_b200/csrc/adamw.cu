@@ -68,13 +68,15 @@ constexpr int kMaxPeers = 16;
 struct PeerPtrs {
   const float* grad[kMaxPeers];
   __half* p16[kMaxPeers];
+  float* p32[kMaxPeers];  // optional fp32 mirror of the elements [f32_lo, n): the per-slice parameters kernel A reads in fp32
 };
 
 // WORLD > 0: compile-time rank count (all peer loads of an element group are in flight together); 0: run-time loop
 template <int WORLD>
 __global__ void __launch_bounds__(256) adamw_dp_kernel(float* __restrict__ p, const __grid_constant__ PeerPtrs peers, float* __restrict__ m,
-                                                       float* __restrict__ v, int world_rt, int64_t lo, int64_t hi, float lr, float b1, float b2,
-                                                       float eps, float wd, float step_size, float inv_sqrt_bc2, float unscale) {
+                                                       float* __restrict__ v, int world_rt, int64_t lo, int64_t hi, int64_t f32_lo, float lr,
+                                                       float b1, float b2, float eps, float wd, float step_size, float inv_sqrt_bc2,
+                                                       float unscale) {
   const int world = WORLD > 0 ? WORLD : world_rt;
   // lo is a multiple of 4 (16-byte aligned vectors); the ragged tail of the last shard is handled element-wise
   const int64_t n4 = (hi - lo) >> 2;
@@ -120,6 +122,8 @@ __global__ void __launch_bounds__(256) adamw_dp_kernel(float* __restrict__ p, co
     const __half2 h0 = __floats2half2_rn(pv.x, pv.y), h1 = __floats2half2_rn(pv.z, pv.w);
     const uint2 packed = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
     for (int r = 0; r < world; ++r) *reinterpret_cast<uint2*>(peers.p16[r] + e) = packed;
+    if (e >= f32_lo)  // f32_lo and lo are multiples of 4: a vector never straddles the boundary
+      for (int r = 0; r < world; ++r) *reinterpret_cast<float4*>(peers.p32[r] + (e - f32_lo)) = pv;
   }
   for (int64_t e = lo + 4 * n4 + tid; e < hi; e += nth) {
     float g = 0.f;
@@ -130,6 +134,8 @@ __global__ void __launch_bounds__(256) adamw_dp_kernel(float* __restrict__ p, co
     m[e] = mi;
     v[e] = vi;
     for (int r = 0; r < world; ++r) peers.p16[r][e] = __float2half_rn(pi);
+    if (e >= f32_lo)
+      for (int r = 0; r < world; ++r) peers.p32[r][e - f32_lo] = pi;
   }
 }
 
@@ -147,16 +153,21 @@ extern "C" int nsv_adamw_shard_bounds(int64_t n, int world, int rank, int64_t* l
 
 extern "C" int nsv_adamw_step_dp(float* param, const void* const* peer_grads, float* exp_avg, float* exp_avg_sq,
                                  void* const* peer_param_f16, int world, int rank, int64_t n, float lr, float beta1, float beta2,
-                                 float eps, float weight_decay, int step, float grad_unscale, void* stream) {
+                                 float eps, float weight_decay, int step, float grad_unscale, int64_t f32_lo,
+                                 void* const* peer_param_f32, void* stream) {
   using namespace nsv;
   NSV_REQUIRE(n >= 0 && step >= 1, "nsv_adamw_step_dp: bad n / step");
   NSV_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "nsv_adamw_step_dp: world must be 1..16, rank in [0, world)");
   NSV_REQUIRE(param && peer_grads && exp_avg && exp_avg_sq && peer_param_f16, "nsv_adamw_step_dp: NULL pointer");
+  if (!peer_param_f32) f32_lo = n;  // no fp32 mirror
+  NSV_REQUIRE(f32_lo >= 0 && f32_lo % 4 == 0, "nsv_adamw_step_dp: f32_lo must be a non-negative multiple of 4");
   PeerPtrs pp;
   for (int r = 0; r < kMaxPeers; ++r) {
     pp.grad[r] = r < world ? (const float*)peer_grads[r] : nullptr;
     pp.p16[r] = r < world ? (__half*)peer_param_f16[r] : nullptr;
+    pp.p32[r] = (r < world && peer_param_f32) ? (float*)peer_param_f32[r] : nullptr;
     NSV_REQUIRE(r >= world || (pp.grad[r] && pp.p16[r]), "nsv_adamw_step_dp: NULL peer pointer");
+    NSV_REQUIRE(r >= world || f32_lo >= n || (pp.p32[r] && (uintptr_t)pp.p32[r] % 16 == 0), "nsv_adamw_step_dp: NULL / unaligned fp32 mirror pointer");
   }
   int64_t lo = 0, hi = 0;
   nsv_adamw_shard_bounds(n, world, rank, &lo, &hi);
@@ -166,7 +177,7 @@ extern "C" int nsv_adamw_step_dp(float* param, const void* const* peer_grads, fl
   const int64_t blocks = ((hi - lo) / 4 + 255) / 256 + 1;
   const int grid = (int)(blocks < (int64_t)num_sms() * 8 ? blocks : (int64_t)num_sms() * 8);
 #define NSV_DP_LAUNCH(W)                                                                                                            \
-  adamw_dp_kernel<W><<<grid, 256, 0, (cudaStream_t)stream>>>(param, pp, exp_avg, exp_avg_sq, world, lo, hi, lr, beta1, beta2, eps, weight_decay, \
+  adamw_dp_kernel<W><<<grid, 256, 0, (cudaStream_t)stream>>>(param, pp, exp_avg, exp_avg_sq, world, lo, hi, f32_lo, lr, beta1, beta2, eps, weight_decay, \
                                                              step_size, inv_sqrt_bc2, grad_unscale)
   if (world == 2) NSV_DP_LAUNCH(2);
   else if (world == 4) NSV_DP_LAUNCH(4);

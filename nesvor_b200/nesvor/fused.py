@@ -133,6 +133,10 @@ class FusedState:
             if train:
                 self.n_train = off
         self.n_total = off
+        # per-slice parameters (everything behind the MLP weights) are read by kernel A in fp32: under the peer-memory
+        # optimiser every rank keeps a current fp32 mirror of them (`tail32`, see enable_peer_memory / seg)
+        self.tail_lo = (self.offsets["mlp"].stop + 3) // 4 * 4
+        self.tail32: Optional[torch.Tensor] = None
         self.flat = torch.zeros(self.n_total, dtype=torch.float32, device=dev)
         self.flat16 = torch.zeros(self.n_total, dtype=torch.float16, device=dev)
         self.grad = torch.zeros(self.n_total + 8, dtype=torch.float32, device=dev)  # + losses[8]
@@ -149,27 +153,37 @@ class FusedState:
 
         n_grad = self.grad.numel() * 4
         n_grad_pad = (n_grad + 255) // 256 * 256
-        nbytes = n_grad_pad + self.flat16.numel() * 2
+        n_f16_pad = (self.flat16.numel() * 2 + 255) // 256 * 256
+        n_tail = self.n_total - self.tail_lo
+        nbytes = n_grad_pad + n_f16_pad + n_tail * 4
         buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
         handle = symm_mem.rendezvous(buf, group)
         grad = buf[:n_grad].view(torch.float32)
-        flat16 = buf[n_grad_pad:nbytes].view(torch.float16)
+        flat16 = buf[n_grad_pad : n_grad_pad + self.flat16.numel() * 2].view(torch.float16)
         grad.zero_()
         flat16.copy_(self.flat16)
         self.grad, self.flat16 = grad, flat16
+        if n_tail > 0:  # only the owner of a shard updates its fp32 master: the owner mirrors the per-slice parameters everywhere
+            tail32 = buf[n_grad_pad + n_f16_pad : nbytes].view(torch.float32)
+            tail32.copy_(self.flat[self.tail_lo :])
+            self.tail32 = tail32
         self.losses = self.grad[self.n_total : self.n_total + 8]
         self._symm_buf, self.peer_handle = buf, handle
         world = handle.world_size
         ptrs = [int(p) for p in handle.buffer_ptrs]
         self.peer_grads = (ctypes.c_void_p * world)(*ptrs)
         self.peer_flat16 = (ctypes.c_void_p * world)(*[p + n_grad_pad for p in ptrs])
+        self.peer_tail32 = (ctypes.c_void_p * world)(*[p + n_grad_pad + n_f16_pad for p in ptrs]) if n_tail > 0 else None
         handle.barrier()  # every rank's copy is initialised before anyone's optimiser writes into it
 
     # ------------------------------------------------------------------ model <-> flat
     def seg(self, name: str, buf: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         if name not in self.offsets:
             return None
-        return (self.flat if buf is None else buf)[self.offsets[name]]
+        sl = self.offsets[name]
+        if buf is None and self.tail32 is not None and sl.start >= self.tail_lo:
+            return self.tail32[sl.start - self.tail_lo : sl.stop - self.tail_lo]
+        return (self.flat if buf is None else buf)[sl]
 
     def pull_from_model(self) -> None:
         with torch.no_grad():
@@ -390,7 +404,7 @@ class FusedTrainer:
                     _lib.ptr(st.flat), st.peer_grads, _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), st.peer_flat16,
                     ctypes.c_int(world), ctypes.c_int(rank), ctypes.c_int64(st.n_train), ctypes.c_float(self.lr), ctypes.c_float(0.9),
                     ctypes.c_float(0.99), ctypes.c_float(1e-15), ctypes.c_float(1e-2), ctypes.c_int(self.iteration),
-                    ctypes.c_float(1.0 / world), _lib.stream(st.device))
+                    ctypes.c_float(1.0 / world), ctypes.c_int64(st.tail_lo), st.peer_tail32, _lib.stream(st.device))
             _lib.check(rc, "nsv_adamw_step_dp")
             h.barrier()  # every owner has read this rank's gradient and written this rank's fp16 parameters
             st.grad[: st.n_train].zero_()

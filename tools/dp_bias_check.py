@@ -95,8 +95,14 @@ def main():
     dist.broadcast(ref, src=0)
     same = bool((ref == trainer.state.flat16[:n]).all())
     finite = all(bool(torch.isfinite(x)) for x in last.values())
-    out.update(dp_mode=trainer.dp_mode, replicas_identical=same, losses_after_3_steps={k: float(x) for k, x in last.items()})
-    ok = ok and same and finite and "biasReg" in last
+    # batch-independent terms must agree across ranks (they read the per-slice fp32 parameters every rank mirrors)
+    tr = torch.stack([last["transReg"].detach().float().reshape(()), last["biasReg"].detach().float().reshape(())])
+    tr_all = [torch.empty_like(tr) for _ in range(world)]
+    dist.all_gather(tr_all, tr)
+    consistent = all(bool(torch.equal(t, tr_all[0])) for t in tr_all)
+    out.update(dp_mode=trainer.dp_mode, replicas_identical=same, rank_independent_terms_identical=consistent,
+               losses_after_3_steps={k: float(x) for k, x in last.items()})
+    ok = ok and same and finite and consistent and "biasReg" in last
     print(json.dumps(out), flush=True)
     dist.barrier()
     dist.destroy_process_group()

@@ -45,6 +45,10 @@ def main():
     g = torch.Generator().manual_seed(100 + rank)
     P = dataset.xyz.shape[0]
     tp, ta = trainers["peer"], trainers["allreduce"]
+    for name in ("slice_embedding", "logit_coef", "log_var_slice", "axisangle"):
+        t = tp.state.seg(name)
+        if t is not None:
+            setattr(tp, "_initial_" + name, t.clone())
     for it in range(6):
         sel = torch.randint(0, P, (args.batch_size,), generator=g).to(dev)
         noise = torch.randn(args.batch_size, args.n_samples, 3, generator=g).to(dev)
@@ -66,6 +70,14 @@ def main():
     n = tp.state.n_train
     d16 = (tp.state.flat16[:n].float() - ta.state.flat16[:n].float()).abs().max().item()
     changed = (tp.state.flat16[:n] != 0).float().mean().item()
+    # the per-slice parameters kernel A reads in fp32 (slice embedding, slice scale / variance, poses) must be current on
+    # EVERY rank, not only on the owner of their optimiser shard (fp32 mirror written by nsv_adamw_step_dp)
+    d_tail = 0.0
+    for name in ("slice_embedding", "logit_coef", "log_var_slice", "axisangle"):
+        pa, pb = tp.state.seg(name), ta.state.seg(name)
+        if pa is not None and pa.numel():
+            d_tail = max(d_tail, (pa - pb).abs().max().item())
+            assert (pa != getattr(tp, "_initial_" + name)).any(), name + " did not move"
     tp.sync_to_model()
     ta.sync_to_model()
     d32 = (tp.state.flat[:n] - ta.state.flat[:n]).abs().max().item()
@@ -74,10 +86,11 @@ def main():
     ref = tp.state.flat16[:n].clone()
     dist.broadcast(ref, src=0)
     same = bool((ref == tp.state.flat16[:n]).all())
-    out = dict(rank=rank, world=world, max_abs_diff_fp16=d16, max_abs_diff_fp32_master=d32, param_scale=scale, replicas_identical=same,
-               nonzero_frac=changed)
+    out = dict(rank=rank, world=world, max_abs_diff_fp16=d16, max_abs_diff_fp32_master=d32, max_abs_diff_per_slice_fp32=d_tail,
+               param_scale=scale, replicas_identical=same, nonzero_frac=changed)
     print(json.dumps(out), flush=True)
     ok = same and d16 <= (0.0 if world == 2 else 2e-3 * scale) and d32 <= (0.0 if world == 2 else 1e-4 * scale)
+    ok = ok and d_tail <= (0.0 if world == 2 else 1e-4 * scale)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
