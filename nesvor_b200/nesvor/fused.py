@@ -307,9 +307,11 @@ class FusedState:
 class FusedTrainer:
     """Drop-in for the body of train()'s loop: `losses = trainer.step(xyz=..., v=..., slice_idx=...)`."""
 
-    def __init__(self, model: NeSVoR, args: Namespace):
+    def __init__(self, model: NeSVoR, args: Namespace, batch_size: Optional[int] = None):
+        """`batch_size`: pixels per call of `step` / `step_distributed` on THIS rank (default args.batch_size); it only
+        sets the power-of-two loss scale of the fp16 backward operands."""
         self.model, self.args = model, args
-        self.state = FusedState(model.inr, args, model, n_batch_samples=args.batch_size * args.n_samples)
+        self.state = FusedState(model.inr, args, model, n_batch_samples=(batch_size or args.batch_size) * args.n_samples)
         st = self.state
         self.exp_avg = torch.zeros(st.n_train, dtype=torch.float32, device=st.device)
         self.exp_avg_sq = torch.zeros(st.n_train, dtype=torch.float32, device=st.device)

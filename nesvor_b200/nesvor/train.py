@@ -6,6 +6,11 @@ AdamW with two groups, MultiStepLR on milestones, GradScaler(init_scale=1), loss
 of moving averages, outputs).  The per-iteration compute is delegated to `NeSVoR.forward`
 (autograd-composed native ops) or, when `args.fused` is set and the configuration is supported,
 to the fused kernel + fused AdamW (`fused.FusedTrainer`).
+
+Data parallelism (the reference is single-GPU): when `torch.distributed` is initialised with more than
+one rank, `train` keeps the pixel table replicated, makes every rank draw the SAME global batch of `args.batch_size`
+pixels (the epoch permutation is broadcast from rank 0), hands rank r the r-th contiguous chunk of it and steps with
+`FusedTrainer.step_distributed` (gradient mean + AdamW over NVLink peer memory or one NCCL all-reduce).
 """
 from argparse import Namespace
 from typing import Dict, List, Tuple
@@ -40,6 +45,7 @@ class Dataset(object):
         self.resolution = torch.stack(resolution_all, 0)
         self.count = self.v.shape[0]
         self.epoch = 0
+        self.dist = None  # set by train() under data parallelism: the epoch permutation is then broadcast from rank 0
 
     @property
     def xyz_transformed(self) -> torch.Tensor:
@@ -62,6 +68,8 @@ class Dataset(object):
             self.count = 0
             self.epoch += 1
             idx = torch.randperm(self.xyz.shape[0], device=device)
+            if self.dist is not None:
+                self.dist.broadcast(idx, src=0)
             self.xyz, self.v, self.slice_idx = self.xyz[idx], self.v[idx], self.slice_idx[idx]
         sl = slice(self.count, self.count + batch_size)
         self.count += batch_size
@@ -106,10 +114,25 @@ def train(slices: List[Slice], args: Namespace) -> Tuple[INR, List[Slice], Volum
     dataset = Dataset(slices, args)
     model = NeSVoR(dataset.transformation, dataset.resolution, dataset.mean, dataset.bounding_box, args)
     use_fused = bool(getattr(args, "fused", False))
+    import torch.distributed as dist
+
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    if world > 1:
+        from .distributed import shard_batch
+
+        if not use_fused:
+            raise RuntimeError("data-parallel training runs on the fused path: set args.fused")
+        if args.batch_size % world:
+            raise RuntimeError(f"args.batch_size ({args.batch_size}) must be a multiple of the number of ranks ({world})")
+        dataset.dist = dist
+        with torch.no_grad():  # replicas start from rank 0's initialisation (nn.Embedding draws from the global RNG)
+            for p in model.parameters():
+                dist.broadcast(p.data, src=0)
     if use_fused:
         from .fused import FusedTrainer
 
-        trainer = FusedTrainer(model, args)
+        trainer = FusedTrainer(model, args, batch_size=args.batch_size // world)
     else:
         optimizer = build_optimizer(model, args)
         scheduler = optim.lr_scheduler.MultiStepLR(optimizer=optimizer, milestones=list(range(1, len(args.milestones) + 1)), gamma=args.gamma)
@@ -124,7 +147,9 @@ def train(slices: List[Slice], args: Namespace) -> Tuple[INR, List[Slice], Volum
     for i in range(1, args.n_iter + 1):
         t0 = time.time()
         batch = dataset.get_batch(args.batch_size, args.device)
-        if use_fused:
+        if world > 1:
+            losses = trainer.step_distributed(dist, world, **shard_batch(batch, rank, world))
+        elif use_fused:
             losses = trainer.step(**batch)
         else:
             losses = model(**batch)

@@ -33,3 +33,14 @@ def test_bias_field_head_data_parallel(native_lib):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     print(r.stdout[-3000:], r.stderr[-2000:])
     assert r.returncode == 0
+
+
+def test_train_is_data_parallel_under_a_process_group(native_lib):
+    """`train(slices, args)` inside a 2-rank NCCL group (tools/dp_train_check.py): replicas identical, phantom reconstructed."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29535", os.path.join(ROOT, "tools", "dp_train_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    print(r.stdout[-3000:], r.stderr[-2000:])
+    assert r.returncode == 0
