@@ -174,6 +174,51 @@ def kernel_b_leg(dev, flush, reps=5):
             "ms": ms, "pixels_per_s": n_px / (ms * 1e-3), "algorithmic_bytes": alg, "achieved": alg / (ms * 1e-3) / 1e9, "unit": "GB/s"}
 
 
+def other_heads_leg(dev, steps=50):
+    """Whole fused iteration (kernel A [+ the mean(log_bias) pre-pass] + finalize + transReg + AdamW, device-resident batches)
+    at 2^20 queries for the head configurations of BASELINE configs 3 and 5 -- informative only; the bench line's
+    `value` stays config 2.  cfg3: 128^3 phantom, 3 stacks with injected motion, reference-default heads (sigma_net,
+    slice scale / variance, pose optimisation), S = 256.  cfg5: 138^3 phantom at 0.8 mm, 9 stacks x 30 slices, the same
+    heads + bias field on 4 levels (b_net), finest resolution 0.5."""
+    import torch
+    import nesvor_b200 as nb
+    from nesvor_b200.data.phantom import simulate_slices
+    from nesvor_b200.nesvor.fused import FusedTrainer
+    from nesvor_b200.nesvor.train import Dataset
+
+    heads = dict(depth=1, no_pixel_variance=False, no_slice_variance=False, no_transformation_optimization=False, n_levels=None,
+                 n_samples=256, batch_size=4096)
+    cases = {"cfg3_heads": (dict(heads), dict(n=128, n_stacks=3, res_r=1.0, res_s=1.0, gap=3.0, motion_deg=3.0, motion_mm=1.5)),
+             "cfg5_heads": (dict(heads, n_levels_bias=4, finest_resolution=0.5), dict(n=138, n_stacks=9, res_r=0.8, res_s=0.8, gap=3.0, n_slice=30))}
+    out = {}
+    for name, (kw, sim) in cases.items():
+        try:
+            args = make_args(dev, **kw)
+            torch.manual_seed(0)
+            slices, _, _ = simulate_slices(device=dev, **sim)
+            dataset = Dataset(slices, args)
+            model = nb.NeSVoR(dataset.transformation, dataset.resolution, dataset.mean, dataset.bounding_box, args)
+            trainer = FusedTrainer(model, args)
+            B, S = args.batch_size, args.n_samples
+            for _ in range(10):
+                trainer.step(**dataset.get_batch(B, dev))
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                losses = trainer.step(**dataset.get_batch(B, dev))
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"ms_per_step": ms, "queries_per_s": B * S / (ms * 1e-3), "n_levels": int(trainer.state.cfg.grid.n_levels),
+                         "n_slices": int(model.n_slices), "batch_size": B, "n_samples": S,
+                         "losses_last_step": {k: float(v) for k, v in losses.items()}}
+            del trainer, model, dataset, slices
+        except Exception as e:  # informative leg: never take the bench line down with it
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    return out
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(a):
     import torch
@@ -293,6 +338,7 @@ def run_ours(a):
             durs.append(k0.elapsed_time(k1))
     k_ms = sum(durs) / len(durs)
     kernel_b = kernel_b_leg(dev, flush)
+    other_heads = other_heads_leg(dev) if world == 1 else None
     clocks.__exit__(None, None, None)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -321,6 +367,8 @@ def run_ours(a):
             "gpu_launches": 3 * a.steps, "roofline": roofline, "kernel_b": dict(kernel_b, frac=kernel_b["achieved"] / peak, peak=peak),
             "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "losses_last_step": {k: float(v) for k, v in losses.items()}}
+    if other_heads is not None:
+        line["other_heads"] = other_heads
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

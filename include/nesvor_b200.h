@@ -45,6 +45,11 @@ int nsv_axisangle2mat_fwd_f32(const float* axisangle, float* mat, int n, void* s
 int nsv_axisangle2mat_bwd_f32(const float* grad_mat, const float* axisangle, float* grad_axisangle, int n, void* stream);
 int nsv_mat2axisangle_fwd_f32(const float* mat, float* axisangle, int n, void* stream);
 int nsv_mat2axisangle_bwd_f32(const float* mat, const float* grad_axisangle, float* grad_mat, int n, void* stream);
+/* transReg of the training loop and its gradient in one launch (replaces NeSVoR.trans_loss, nesvor/nesvor/models.py:357-363,
+ * composed there from RigidTransform.inv / compose / axisangle under autograd): err = axisangle(T_init^-1 o T) per slice,
+ * loss = mean(err_R^2) + 1e-3 mean(err_T^2).  ACCUMULATES: grad_axisangle[n,6] += weight * dloss/daxisangle, *loss += loss. */
+int nsv_trans_reg_f32(const float* axisangle /* [n,6] */, const float* axisangle_init /* [n,6] */, float* grad_axisangle,
+                      float* loss, int n, float weight, void* stream);
 int nsv_axisangle2mat_fwd_f64(const double* axisangle, double* mat, int n, void* stream);
 int nsv_axisangle2mat_bwd_f64(const double* grad_mat, const double* axisangle, double* grad_axisangle, int n, void* stream);
 int nsv_mat2axisangle_fwd_f64(const double* mat, double* axisangle, int n, void* stream);

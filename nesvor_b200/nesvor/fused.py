@@ -344,17 +344,18 @@ class FusedTrainer:
     def decay_lr(self, gamma: float) -> None:
         self.lr *= gamma
 
-    def _trans_reg(self) -> torch.Tensor:
-        """transReg (models.py:357-363) on the flat axisangle; its gradient is added to the flat grad."""
+    def _trans_reg(self) -> None:
+        """transReg (models.py:357-363) and its gradient in one native launch (`nsv_trans_reg_f32`): the weighted gradient is
+        added to the flat grad's axisangle segment, the loss value lands in losses[5]."""
         st = self.state
-        ax = st.seg("axisangle").view(-1, 6).detach().clone().requires_grad_(True)
-        x = RigidTransform(ax, trans_first=True)
-        y = RigidTransform(self.model.axisangle_init, trans_first=True)
-        err = y.inv().compose(x).axisangle(trans_first=True)
-        loss = torch.mean(err[:, :3] ** 2) + 1e-3 * torch.mean(err[:, 3:] ** 2)
-        (g,) = torch.autograd.grad(loss, ax)
-        st.seg("axisangle", st.grad).add_(g.reshape(-1), alpha=float(self.args.weight_transformation))
-        return loss.detach()
+        if not hasattr(self, "_axisangle_init"):
+            self._axisangle_init = self.model.axisangle_init.detach().to(st.device, torch.float32).contiguous()
+        with torch.cuda.device(st.device):
+            rc = _lib.lib().nsv_trans_reg_f32(
+                _lib.ptr(st.seg("axisangle")), _lib.ptr(self._axisangle_init), _lib.ptr(st.seg("axisangle", st.grad)),
+                ctypes.c_void_p(st.losses.data_ptr() + 20), ctypes.c_int(self.model.n_slices),
+                ctypes.c_float(float(self.args.weight_transformation)), _lib.stream(st.device))
+        _lib.check(rc, "nsv_trans_reg_f32")
 
     def step(self, xyz, v, slice_idx, noise=None) -> Dict[str, torch.Tensor]:
         st, a = self.state, self.args
@@ -362,9 +363,12 @@ class FusedTrainer:
         st.losses.zero_()  # parameter gradients were cleared by the previous AdamW pass
         n_q = xyz.shape[0] * a.n_samples
         losses, _ = st.forward_backward(xyz, v, slice_idx, noise, seed=self.seed, offset=(self.iteration - 1) * n_q)
-        out = st.loss_dict(losses.clone())
         if self.pose and a.weight_transformation:
-            out[T_REG] = self._trans_reg()
+            self._trans_reg()
+        snap = losses.clone()  # one copy of the step's loss values (the buffer is cleared by the next step)
+        out = st.loss_dict(snap)
+        if self.pose and a.weight_transformation:
+            out[T_REG] = snap[5]
         with torch.cuda.device(st.device):
             rc = _lib.lib().nsv_adamw_step(
                 _lib.ptr(st.flat), _lib.ptr(st.grad), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), _lib.ptr(st.flat16),
@@ -386,9 +390,12 @@ class FusedTrainer:
         rank = dist.get_rank()
         losses, _ = st.forward_backward(xyz, v, slice_idx, noise, seed=self.seed + 7919 * rank,
                                         offset=(self.iteration - 1) * n_q, dist=dist, world=world)
-        out = st.loss_dict(losses.clone())
         if self.pose and a.weight_transformation:
-            out[T_REG] = self._trans_reg()  # identical on every rank: the all-reduce mean leaves it unchanged
+            self._trans_reg()  # identical on every rank: the all-reduce mean leaves it unchanged
+        snap = losses.clone()
+        out = st.loss_dict(snap)
+        if self.pose and a.weight_transformation:
+            out[T_REG] = snap[5]
         self._dp_update(dist, world)
         return out
 

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import REF_AXISANGLES, scipy_axisangle2mat
+from helpers import REF_AXISANGLES, rel_l2, scipy_axisangle2mat
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -78,3 +78,48 @@ def test_autograd_and_rigid_transform(native_lib):
     assert nb.axisangle2mat(torch.zeros(0, 6, device="cuda")).shape == (0, 3, 4)
     with pytest.raises(RuntimeError, match="contiguous"):
         nb.axisangle2mat(torch.zeros(6, 4, device="cuda").t())
+
+
+def test_trans_reg_matches_autograd_composition_and_oracle(native_lib):
+    """nsv_trans_reg_f32 (transReg + gradient in one launch; NeSVoR.trans_loss, models.py:357-363) vs (a) the same loss
+    composed from RigidTransform.inv / compose / axisangle under autograd over the native converters and (b) the CPU
+    oracle's trans_loss.  Cases: small and large relative motions, identical poses (zero error: the converters' first-order
+    branches), large relative rotations.  fp32 tolerance 2e-5 relative on the loss, 2e-4 relative L2 on the gradient."""
+    import ctypes
+
+    import nesvor_b200 as nb
+    from nesvor_b200 import _lib
+    from oracle import inr_oracle as io
+
+    g = torch.Generator().manual_seed(4)
+    n = 300
+    ax0 = torch.randn(n, 6, generator=g) * torch.tensor([0.8, 0.8, 0.8, 20.0, 20.0, 20.0])
+    d = torch.randn(n, 6, generator=g) * torch.tensor([0.05, 0.05, 0.05, 1.0, 1.0, 1.0])
+    d[:50] *= 10.0   # large relative motion (rotations of ~1 rad, translations of ~10 mm)
+    d[50:60] = 0.0   # identical poses
+    d[60:70] *= 1e-4  # nearly identical
+    ax = ax0 + d
+    for weight in (1.0, 0.1):
+        a_dev, a0_dev = ax.cuda().contiguous(), ax0.cuda().contiguous()
+        grad = torch.full((n, 6), 0.5, device="cuda")  # the kernel accumulates
+        loss = torch.full((1,), 2.0, device="cuda")
+        rc = _lib.lib().nsv_trans_reg_f32(_lib.ptr(a_dev), _lib.ptr(a0_dev), _lib.ptr(grad), _lib.ptr(loss), ctypes.c_int(n),
+                                          ctypes.c_float(weight), _lib.stream(a_dev.device))
+        _lib.check(rc, "nsv_trans_reg_f32")
+        torch.cuda.synchronize()
+        # (a) autograd over the native converters
+        x_ax = a_dev.clone().requires_grad_(True)
+        x, y = nb.RigidTransform(x_ax, True), nb.RigidTransform(a0_dev, True)
+        err = y.inv().compose(x).axisangle(True)
+        ref = torch.mean(err[:, :3] ** 2) + 1e-3 * torch.mean(err[:, 3:] ** 2)
+        (gref,) = torch.autograd.grad(ref, x_ax)
+        assert abs(float(loss) - 2.0 - float(ref)) <= 2e-5 * abs(float(ref))
+        assert rel_l2((grad - 0.5).cpu(), (weight * gref).cpu()) < 2e-4
+        # (b) CPU oracle
+        xo = ax.clone().requires_grad_(True)
+        e = io.mat2axisangle(io.mat_compose(io.mat_inv(io.axisangle2mat(ax0)), io.axisangle2mat(xo)))
+        lo = torch.mean(e[:, :3] ** 2) + 1e-3 * torch.mean(e[:, 3:] ** 2)
+        (go,) = torch.autograd.grad(lo, xo)
+        assert abs(float(loss) - 2.0 - float(lo)) <= 5e-5 * abs(float(lo))
+        assert rel_l2((grad - 0.5).cpu(), weight * go) < 1e-3
+    assert _lib.lib().nsv_trans_reg_f32(None, None, None, None, ctypes.c_int(0), ctypes.c_float(1.0), None) == 0

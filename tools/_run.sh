@@ -1,3 +1,5 @@
 set -x
 mkdir -p gpurun_out
-timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29535 tools/dp_train_check.py 2>&1 | grep -v "^$" | tail -8 | tee gpurun_out/r1g_dp_train_check.log
+timeout 200 python -m pytest tests/test_gpu_pose.py tests/test_gpu_e2e.py -q 2>&1 | tail -4 | tee gpurun_out/r1i_tests.log
+timeout 100 python __graft_entry__.py smoke 2>&1 | tail -1 | tee gpurun_out/r1i_smoke.log
+timeout 300 python bench.py --steps 300 --warmup 5 2>&1 | tail -1 | tee gpurun_out/r1i_bench.log
