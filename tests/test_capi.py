@@ -84,3 +84,34 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dp, f)
+
+
+def test_bias_mean_and_trans_reg_reject_bad_arguments_without_gpu(native_lib):
+    """nsv_inr_bias_mean / nsv_trans_reg_f32 validate on the host before any launch (no GPU here)."""
+    from nesvor_b200 import _lib
+
+    native_lib.nsv_last_error_string.restype = ctypes.c_char_p
+    cfg, prm = _lib.InrConfig(), _lib.InrParams()
+    rc = native_lib.nsv_inr_bias_mean(ctypes.byref(cfg), ctypes.byref(prm), None, None, None, ctypes.c_uint64(0), ctypes.c_uint64(0), None,
+                                      ctypes.c_int64(8), ctypes.c_int(32), None)
+    assert rc == -1 and b"NULL" in native_lib.nsv_last_error_string()  # NSV_EINVAL
+    # a configuration outside the instantiation: non-NULL (never dereferenced) pointers, n_levels_bias = 5
+    meta, _ = _lib.make_grid_meta(12, 2, 19, 7, 1.3819)
+    cfg.grid, cfg.width, cfg.depth, cfg.n_features_slice, cfg.n_levels_bias, cfg.pixel_variance = meta, 64, 1, 16, 5, 1
+    fake = ctypes.c_void_p(256)
+    for f in ("table_f16", "mlp_f16", "axisangle", "psf_sigma", "slice_embedding"):
+        setattr(prm, f, 256)
+    rc = native_lib.nsv_inr_bias_mean(ctypes.byref(cfg), ctypes.byref(prm), fake, fake, None, ctypes.c_uint64(0), ctypes.c_uint64(0), fake,
+                                      ctypes.c_int64(8), ctypes.c_int(32), None)
+    assert rc == -2 and b"n_levels_bias" in native_lib.nsv_last_error_string()  # NSV_EUNSUPPORTED
+    cfg.n_levels_bias = 4
+    rc = native_lib.nsv_inr_bias_mean(ctypes.byref(cfg), ctypes.byref(prm), fake, fake, None, ctypes.c_uint64(0), ctypes.c_uint64(0), fake,
+                                      ctypes.c_int64(8), ctypes.c_int(48), None)
+    assert rc == -1 and b"power of two" in native_lib.nsv_last_error_string()
+    # packed MLP layout with the bias head: density | sigma | bias, each 64*32 + 16*64 halves at width 64, depth 1
+    off = (ctypes.c_int64 * 3)()
+    native_lib.nsv_inr_mlp_layout.restype = ctypes.c_int64
+    assert native_lib.nsv_inr_mlp_layout(ctypes.byref(cfg), off) == 3 * 3072 and list(off) == [0, 3072, 6144]
+    assert native_lib.nsv_trans_reg_f32(None, None, None, None, ctypes.c_int(0), ctypes.c_float(1.0), None) == 0
+    assert native_lib.nsv_trans_reg_f32(None, None, None, None, ctypes.c_int(3), ctypes.c_float(1.0), None) == -1
+    assert native_lib.nsv_trans_reg_f32(None, None, None, None, ctypes.c_int(-1), ctypes.c_float(1.0), None) == -1

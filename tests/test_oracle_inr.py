@@ -101,3 +101,77 @@ def test_analytic_loss_gradients_of_appendix_b():
         gc = torch.zeros(ns, dtype=torch.float64).index_add_(0, k, m * d_vhat)
         cs = torch.softmax(logit, 0) * ns
         torch.testing.assert_close(glogit, cs * (gc - (gc * cs).sum() / ns))
+
+
+def test_analytic_gradients_of_the_bias_field_head():
+    """The bias-field formulas kernel A implements (DESIGN s.4: v_out = c mean(exp(lb) rho), var through the DETACHED bias,
+    biasReg = mean(lb)^2 with one batch-wide cotangent) vs autograd on the reference's op sequence (models.py:286-323), fp64."""
+    torch.manual_seed(1)
+    B, S, ns = 6, 8, 3
+    z0 = torch.randn(B, S, dtype=torch.float64, requires_grad=True)
+    lv = (torch.randn(B, S, dtype=torch.float64) * 0.3).requires_grad_(True)
+    lb = (torch.randn(B, S, dtype=torch.float64) * 0.4).requires_grad_(True)
+    lvs = (torch.randn(ns, dtype=torch.float64) * 0.3).requires_grad_(True)
+    logit = (torch.randn(ns, dtype=torch.float64) * 0.3).requires_grad_(True)
+    k = torch.randint(0, ns, (B,))
+    v = torch.rand(B, dtype=torch.float64)
+    w_b = 100.0
+    rho = torch.nn.functional.softplus(z0)
+    bias = lb.exp()
+    c = torch.softmax(logit, 0)[k] * ns
+    vhat = c * (bias * rho).mean(-1)
+    var = (c.detach() * (bias.detach() * lv.exp()).mean(-1)) ** 2 + lvs.exp()[k]
+    loss = ((vhat - v) ** 2 / (2 * var)).mean() + 0.5 * var.log().mean() + w_b * lb.mean() ** 2
+    gz0, glv, glb, glogit = torch.autograd.grad(loss, (z0, lv, lb, logit))
+    with torch.no_grad():
+        e = vhat - v
+        d_vhat = (e / (B * var))[:, None]
+        d_var = ((0.5 / var - 0.5 * e * e / var**2) / B)[:, None]
+        ck = c[:, None]
+        r = ck * (bias * lv.exp()).mean(-1, keepdim=True)
+        torch.testing.assert_close(gz0, torch.sigmoid(z0) * (ck * d_vhat / S * bias))
+        torch.testing.assert_close(glv, (bias * lv.exp() / S) * ck * 2 * r * d_var)
+        torch.testing.assert_close(glb, ck * d_vhat / S * bias * rho + w_b * 2 * lb.mean() / (B * S))
+        m = (bias * rho).mean(-1)
+        gc = torch.zeros(ns, dtype=torch.float64).index_add_(0, k, m * d_vhat[:, 0])
+        cs = torch.softmax(logit, 0) * ns
+        torch.testing.assert_close(glogit, cs * (gc - (gc * cs).sum() / ns))
+
+
+def test_oracle_bias_head_wiring():
+    """OracleNeSVoR with n_levels_bias: b_net sees [slice embedding | first n_levels_bias levels] (models.py:344-347) and
+    nothing else -- perturbing finer levels leaves log_bias (hence biasReg) unchanged, perturbing the coarse ones does not;
+    the gradient of biasReg alone reaches b_net, the slice embedding, the coarse levels and the poses only."""
+    cfg = io.INRConfig(n_levels=6, base_resolution=5, level_scale=1.5, log2_hashmap_size=12, width=32, depth=1, n_levels_bias=2,
+                       n_samples=8, no_transformation_optimization=False)
+    g = torch.Generator().manual_seed(5)
+    ns, B, S = 4, 12, 8
+    ax = torch.randn(ns, 6, generator=g) * torch.tensor([0.1, 0.1, 0.1, 2.0, 2.0, 2.0])
+    res = torch.tensor([[1.0, 1.0, 3.0]]).repeat(ns, 1)
+    bb = torch.tensor([[-20.0, -20.0, -20.0], [20.0, 20.0, 20.0]])
+    om = io.OracleNeSVoR(cfg, ns, ax, res, bb)
+    with torch.no_grad():
+        om.P["table"].copy_(torch.randn(om.P["table"].shape, generator=g) * 0.5)
+    xyz = (torch.rand(B, 3, generator=g) - 0.5) * 20
+    v = torch.rand(B, generator=g)
+    idx = torch.randint(0, ns, (B,), generator=g)
+    noise = torch.randn(B, S, 3, generator=g)
+    l0 = om.forward(xyz, v, idx, noise)
+    assert "biasReg" in l0 and float(l0["biasReg"].detach()) >= 0
+    off = om.meta.offset
+    with torch.no_grad():  # levels >= n_levels_bias do not feed b_net
+        om.P["table"][2 * int(off[2]) :].mul_(1.7)
+    l1 = om.forward(xyz, v, idx, noise)
+    torch.testing.assert_close(l1["biasReg"], l0["biasReg"])
+    assert not torch.allclose(l1["MSE"], l0["MSE"])
+    with torch.no_grad():  # the coarse levels do
+        om.P["table"][: 2 * int(off[2])].mul_(1.7)
+    l2 = om.forward(xyz, v, idx, noise)
+    assert not torch.allclose(l2["biasReg"], l1["biasReg"])
+    # gradient of biasReg alone reaches b_net, the slice embedding, the coarse levels and the poses only
+    (om.forward(xyz, v, idx, noise)["biasReg"]).backward()
+    gt = om.P["table"].grad
+    assert float(gt[: 2 * int(off[2])].abs().sum()) > 0 and float(gt[2 * int(off[2]) :].abs().sum()) == 0
+    assert float(om.P["b_net.w0"].grad.abs().sum()) > 0 and float(om.P["slice_embedding"].grad.abs().sum()) > 0
+    assert float(om.P["axisangle"].grad.abs().sum()) > 0
+    assert om.P["density_net.w0"].grad is None or float(om.P["density_net.w0"].grad.abs().sum()) == 0
