@@ -219,6 +219,48 @@ def other_heads_leg(dev, steps=50):
     return out
 
 
+def unfused_leg(dev, dataset, steps=5):
+    """The same config-2 iteration on the UNFUSED native path -- `NeSVoR.forward` composed from the standalone CUDA ops
+    (hash grid, fused MLP, pose converters) under autograd + torch.optim.AdamW + GradScaler, i.e. the reference's own loop
+    structure (train.py:179-198) with one kernel per op and activations round-tripping HBM.  Informative only: it is what
+    the fused kernel A is measured against on the same GPU (SURVEY s.8d "unfused GPU baseline")."""
+    import torch
+    import nesvor_b200 as nb
+    from nesvor_b200.nesvor.train import build_optimizer, loss_weights
+
+    try:
+        args = make_args(dev, fused=False)
+        torch.manual_seed(0)
+        model = nb.NeSVoR(dataset.transformation, dataset.resolution, dataset.mean, dataset.bounding_box, args)
+        opt = build_optimizer(model, args)
+        scaler = torch.amp.GradScaler("cuda", init_scale=1.0, enabled=True, growth_factor=2.0, backoff_factor=0.5)
+        wts = loss_weights(args)
+        B, S = args.batch_size, args.n_samples
+
+        def it():
+            losses = model(**dataset.get_batch(B, dev))
+            loss = sum(wts[k] * v for k, v in losses.items() if k in wts and wts[k])
+            scaler.scale(loss).backward()
+            scaler.step(opt)
+            scaler.update()
+            opt.zero_grad()
+
+        for _ in range(2):
+            it()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            it()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"ms_per_step": ms, "queries_per_s": B * S / (ms * 1e-3), "steps": steps,
+                "what": "NeSVoR.forward from standalone native ops under autograd + torch.optim.AdamW (config 2, 2^20 queries)"}
+    except Exception as e:  # informative leg: never take the bench line down with it
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(a):
     import torch
@@ -369,6 +411,7 @@ def run_ours(a):
             "losses_last_step": {k: float(v) for k, v in losses.items()}}
     if other_heads is not None:
         line["other_heads"] = other_heads
+        line["unfused_gpu"] = unfused_leg(dev, dataset)  # last: a failure here cannot touch the numbers above
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
