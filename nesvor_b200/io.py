@@ -6,16 +6,19 @@ pickled helper objects (`nesvor.image.image.Volume`, `nesvor.transform.transform
 package's classes (same attribute names), and tiny-cuda-nn's flat parameters are taken over as they are -- the hash
 table is the same level-major `[sum_l T_l, F]` fp32 vector and the MLP the same row-major `[out, in]` layers; only a
 first layer whose input tcnn pads to 16 columns is widened to the 32 columns the kernels are instantiated for.
-NIfTI volumes / slice folders (nibabel) stay out of scope.
+
+`inputs(args)` / `outputs(data, args)` mirror nesvor/cli/io.py:9-49: the argument-driven loading of stacks (+ masks,
+thickness overrides), slice folders and a model checkpoint, and the saving of the output volume (optionally rescaled),
+model, motion-corrected slices and simulated slices -- NIfTI through nesvor_b200.image (no nibabel).
 """
 import pickle
 import types
 from argparse import Namespace
-from typing import Optional, Tuple
+from typing import Any, Dict, Optional, Tuple
 
 import torch
 
-from .image import Volume
+from .image import Volume, load_slices, load_stack, save_slices
 from .nesvor.models import INR
 
 _CLASS_MAP = {
@@ -80,3 +83,38 @@ def load_model(path: str, device, args: Optional[Namespace] = None) -> Tuple[INR
     state["encoding.params"] = state["encoding.params"].float()
     inr.load_state_dict(state)
     return inr.to(device), cp["mask"], merged
+
+
+def inputs(args: Namespace) -> Tuple[Dict[str, Any], Namespace]:
+    """cli/io.py:9-32: {"input_stacks": [Stack], "input_slices": [Slice], "model": INR, "mask": Volume} for whatever of
+    `args.input_stacks` (+ `stack_masks`, `thicknesses`), `args.input_slices`, `args.input_model` is set; with a model the
+    checkpoint's args are merged under the caller's."""
+    out: Dict[str, Any] = {}
+    if getattr(args, "input_stacks", None) is not None:
+        masks, thick = getattr(args, "stack_masks", None), getattr(args, "thicknesses", None)
+        out["input_stacks"] = []
+        for i, f in enumerate(args.input_stacks):
+            stack = load_stack(f, masks[i] if masks is not None else None, device=args.device)
+            if thick is not None:
+                stack.thickness = thick[i]
+            out["input_stacks"].append(stack)
+    if getattr(args, "input_slices", None) is not None:
+        out["input_slices"] = load_slices(args.input_slices, args.device)
+    if getattr(args, "input_model", None) is not None:
+        out["model"], out["mask"], args = load_model(args.input_model, args.device, args)
+    return out, args
+
+
+def outputs(data: Dict[str, Any], args: Namespace) -> None:
+    """cli/io.py:35-49: writes `output_volume` (rescaled to `output_intensity_mean` when set), `output_model`,
+    `output_slices` and `simulated_slices` for the keys present in `data` and named in `args`."""
+    if getattr(args, "output_volume", None) and "output_volume" in data:
+        if getattr(args, "output_intensity_mean", None):
+            data["output_volume"].rescale(args.output_intensity_mean)
+        data["output_volume"].save(args.output_volume)
+    if getattr(args, "output_model", None) and "output_model" in data:
+        save_model(args.output_model, data["output_model"], data["mask"], args)
+    if getattr(args, "output_slices", None) and "output_slices" in data:
+        save_slices(args.output_slices, data["output_slices"])
+    if getattr(args, "simulated_slices", None) and "simulated_slices" in data:
+        save_slices(args.simulated_slices, data["simulated_slices"])

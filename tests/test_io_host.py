@@ -78,3 +78,53 @@ def test_reads_reference_style_checkpoint(tmp_path):
     assert torch.equal(inr.encoding.params.detach(), state["encoding.params"])
     v0, v1 = inr.density_net.weight_views()
     assert torch.equal(v0[:, :16].detach(), w0) and float(v0[:, 16:].detach().abs().max()) == 0.0 and torch.equal(v1.detach(), w1)
+
+
+def test_inputs_outputs_mirror_cli_io(tmp_path):
+    """`outputs` / `inputs` (nesvor/cli/io.py:9-49): volume (rescaled), model, slice folders out; stacks (+ masks,
+    thickness override), slices and model back in, with the checkpoint's args merged under the caller's."""
+    import numpy as np
+
+    from nesvor_b200.image import Volume
+    from nesvor_b200.io import inputs, outputs
+    from nesvor_b200.nesvor.models import INR
+    from nesvor_b200.transform import RigidTransform
+
+    rng = np.random.default_rng(0)
+    args = _args()
+    bb = torch.tensor([[-30.0, -30.0, -30.0], [30.0, 30.0, 30.0]])
+    inr = INR(bb, args)
+    img = torch.tensor(rng.uniform(0.2, 1.0, size=(4, 5, 6)), dtype=torch.float32)
+    ident = torch.tensor([[[1.0, 0, 0, 1.5], [0, 1.0, 0, -2.0], [0, 0, 1.0, 0.5]]])
+    vol = Volume(img.clone(), img > 0.4, RigidTransform(ident, True), 0.8, 0.8, 2.4)
+    pv, pmask = str(tmp_path / "stack.nii.gz"), str(tmp_path / "stack_mask.nii.gz")
+    vol.save(pv, masked=False)
+    Volume(vol.mask.float(), None, vol.transformation, 0.8, 0.8, 2.4).save(pmask, masked=False)
+    # ---- inputs: stacks with masks and a thickness override
+    a_in = Namespace(input_stacks=[pv, pv], stack_masks=[pmask, pmask], thicknesses=[3.0, 4.0], device=torch.device("cpu"))
+    data, a_out = inputs(a_in)
+    assert len(data["input_stacks"]) == 2 and data["input_stacks"][1].thickness == 4.0 and data["input_stacks"][0].gap == 2.4000000953674316
+    assert torch.equal(data["input_stacks"][0].mask[:, 0], vol.mask) and a_out is a_in
+    # ---- outputs: everything named in args and present in data
+    stack = data["input_stacks"][0]
+    out_args = Namespace(**vars(args), output_volume=str(tmp_path / "out.nii.gz"), output_intensity_mean=700.0,
+                         output_model=str(tmp_path / "model.pt"), output_slices=str(tmp_path / "slices"),
+                         simulated_slices=str(tmp_path / "sim"))
+    mean_before = float(vol.image[vol.mask].mean())
+    outputs({"output_volume": vol, "output_model": inr, "mask": vol, "output_slices": stack[:], "simulated_slices": stack[:2]}, out_args)
+    assert abs(float(vol.image[vol.mask].mean()) - 700.0) < 1e-2 and mean_before < 1.0  # rescaled in place like the reference
+    assert sorted(__import__("os").listdir(out_args.output_slices)) == [f"{i}.nii.gz" for i in range(4)]
+    assert len(__import__("os").listdir(out_args.simulated_slices)) == 2
+    # ---- inputs again: slices + model; checkpoint args merged, caller's win
+    a_in2 = Namespace(input_slices=out_args.output_slices, input_model=out_args.output_model, device=torch.device("cpu"), width=32, extra=5)
+    data2, merged = inputs(a_in2)
+    assert len(data2["input_slices"]) == 4 and isinstance(data2["mask"], Volume)
+    for k, v in inr.state_dict().items():
+        assert torch.equal(v, data2["model"].state_dict()[k]), k
+    assert merged.extra == 5 and merged.output_intensity_mean == 700.0 and merged.n_features_z == 15
+    sl = data2["input_slices"][2]
+    np.testing.assert_allclose(sl.transformation.matrix(True).numpy(), stack[2].transformation.matrix(True).numpy(), atol=2e-4)
+    from nesvor_b200.image import load_volume
+
+    back = load_volume(out_args.output_volume)
+    assert torch.allclose(back.image, vol.image * vol.mask, rtol=1e-6)
