@@ -2,7 +2,7 @@
 (nesvor/image/image_utils.py: affine2transformation, transformation2affine, compare_resolution_affine), run in the build
 container where /root/reference exists:
 
-  python tests/golden/make_golden_affine.py        ->  tests/golden/affine_ref.npz
+  python tests/golden/make_golden_affine.py        ->  tests/golden/affine_ref.npz, tests/golden/ncc_ref.npz
 
 image_utils.py imports nibabel (absent here) and `..transform` (whose import JIT-compiles a CUDA extension), but the three
 functions only need numpy, torch and a container with `.matrix(trans_first=True)`: both imports are satisfied with stubs
@@ -86,5 +86,26 @@ def main():
     print("wrote affine_ref.npz:", len(out), "arrays")
 
 
+def make_ncc():
+    """ncc_ref.npz: nesvor/utils/loss.py::ncc_loss (pure torch, imported from the reference file as it lies)."""
+    spec = importlib.util.spec_from_file_location("ref_loss", os.path.join(REF, "nesvor/utils/loss.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = torch.Generator().manual_seed(21)
+    I = torch.rand(5, 1, 12, 14, generator=g)
+    J = 0.6 * I + 0.4 * torch.rand(5, 1, 12, 14, generator=g)
+    mask = torch.rand(5, 1, 12, 14, generator=g) > 0.3
+    V, W = torch.rand(2, 2, 6, 7, 8, generator=g), torch.rand(2, 2, 6, 7, 8, generator=g)
+    out = {"I": I.numpy(), "J": J.numpy(), "mask": mask.numpy(), "V": V.numpy(), "W": W.numpy(),
+           "global_masked": mod.ncc_loss(I, J, mask, win=None, reduction="none").numpy(),
+           "global_plain": mod.ncc_loss(I, J, None, win=None, reduction="none").numpy(),
+           "win9": mod.ncc_loss(I, J, None, win=9).numpy(), "win9_level1_masked": mod.ncc_loss(I, J, mask, win=9, level=1).numpy(),
+           "win5_3d_mean": mod.ncc_loss(V, W, None, win=5, reduction="mean").numpy(),
+           "win5_3d_sum": mod.ncc_loss(V, W, None, win=5, reduction="sum").numpy()}
+    np.savez_compressed(os.path.join(HERE, "ncc_ref.npz"), **out)
+    print("wrote ncc_ref.npz")
+
+
 if __name__ == "__main__":
     main()
+    make_ncc()
