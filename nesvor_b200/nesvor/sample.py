@@ -26,38 +26,43 @@ def _render(model: INR, xyz, transformation, psf_sigma, n_samples: int, args: Na
     return model(xyz_batch, False).mean(-1)
 
 
+def _n_psf_samples(args: Namespace) -> int:
+    return 0 if args.no_output_psf else args.n_inference_samples
+
+
 def sample_volume(model: INR, mask: Volume, args: Namespace) -> Volume:
+    """The INR rendered on the mask's grid resampled to `args.output_resolution` (sample.py:10-14)."""
     model.eval()
-    img = mask.resample(args.output_resolution, None)
-    img.image[img.mask] = sample_points(model, img.xyz_masked, args)
-    return img
+    out = mask.resample(args.output_resolution, None)
+    out.image[out.mask] = sample_points(model, out.xyz_masked, args)
+    return out
 
 
 def sample_points(model: INR, xyz: torch.Tensor, args: Namespace) -> torch.Tensor:
-    shape = xyz.shape[:-1]
-    xyz = xyz.view(-1, 3)
-    v = torch.empty(xyz.shape[0], dtype=torch.float32, device=args.device)
-    batch_size = args.inference_batch_size
-    n = 0 if args.no_output_psf else args.n_inference_samples
+    """PSF-averaged intensities at world points [..., 3], `args.inference_batch_size` points per launch, isotropic output
+    PSF of `args.output_resolution` (sample.py:17-33)."""
+    pts = xyz.reshape(-1, 3)
+    sigma = resolution2sigma(args.output_resolution, isotropic=True)
     with torch.no_grad():
-        for i in range(0, xyz.shape[0], batch_size):
-            v[i : i + batch_size] = _render(model, xyz[i : i + batch_size], None,
-                                            resolution2sigma(args.output_resolution, isotropic=True), n, args)
-    return v.view(shape)
+        vals = [_render(model, chunk, None, sigma, _n_psf_samples(args), args).to(torch.float32)
+                for chunk in pts.split(args.inference_batch_size) if chunk.shape[0]]
+    if not vals:
+        return torch.empty(xyz.shape[:-1], dtype=torch.float32, device=args.device)
+    return torch.cat(vals).view(xyz.shape[:-1])
 
 
 def sample_slice(model: INR, slice: Slice, mask: Volume, args: Namespace) -> Slice:
-    slice_sampled = slice.clone()
-    slice_sampled.image = torch.zeros_like(slice_sampled.image)
-    slice_sampled.mask = torch.zeros_like(slice_sampled.mask)
-    xyz = meshgrid(slice_sampled.shape_xyz, slice_sampled.resolution_xyz).view(-1, 3)
-    m = mask.sample_points(transform_points(slice_sampled.transformation, xyz)) > 0
-    if m.any():
-        n = 0 if args.no_output_psf else args.n_inference_samples
-        v = _render(model, xyz[m], slice_sampled.transformation, resolution2sigma(slice_sampled.resolution_xyz, isotropic=False), n, args)
-        slice_sampled.mask = m.view(slice_sampled.mask.shape)
-        slice_sampled.image[slice_sampled.mask] = v.to(slice_sampled.image.dtype)
-    return slice_sampled
+    """The slice re-simulated from the INR at its own pose and resolution (anisotropic slice PSF), inside `mask` only;
+    pixels outside the mask stay zero and unmasked (sample.py:36-53)."""
+    out = slice.clone(zero=True)
+    grid = meshgrid(out.shape_xyz, out.resolution_xyz).view(-1, 3)
+    inside = mask.sample_points(transform_points(out.transformation, grid)) > 0
+    if inside.any():
+        sigma = resolution2sigma(out.resolution_xyz, isotropic=False)
+        v = _render(model, grid[inside], out.transformation, sigma, _n_psf_samples(args), args)
+        out.mask = inside.view(out.mask.shape)
+        out.image[out.mask] = v.to(out.image.dtype)
+    return out
 
 
 def sample_slices(model: INR, slices: List[Slice], mask: Volume, args: Namespace) -> List[Slice]:
