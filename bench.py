@@ -381,6 +381,16 @@ def run_ours(a):
     k_ms = sum(durs) / len(durs)
     kernel_b = kernel_b_leg(dev, flush)
     other_heads = other_heads_leg(dev) if world == 1 else None
+    if world == 1:  # kernel B next to the reference's own CUDA extension on this GPU (subprocess: foreign kernels stay out of this context)
+        try:
+            import subprocess
+
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "kernel_b_vs_reference.py"), "--reps", "5"],
+                               capture_output=True, text=True, timeout=300)
+            ref_line = next((l for l in reversed(r.stdout.splitlines()) if l.startswith("{")), None)
+            kernel_b["vs_reference_cuda_extension"] = json.loads(ref_line) if ref_line else {"available": False, "why": (r.stderr or "no output")[-200:]}
+        except Exception as e:
+            kernel_b["vs_reference_cuda_extension"] = {"available": False, "why": f"{type(e).__name__}: {e}"[:200]}
     clocks.__exit__(None, None, None)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):

@@ -36,6 +36,24 @@ def build_ref(force=False):
     return REF_SO if os.path.exists(REF_SO) else None
 
 
+REF_GPU_SO = os.path.join(HERE, "_ref", "nesvor_ref_slice_acq_cuda.so")
+
+
+def build_ref_gpu(force=False):
+    """The reference's own slice-acquisition CUDA extension for sm_100a (oracle/build_ref_gpu.sh, ~3 min with torch
+    headers); returns its path, or None when it cannot exist (no /root/reference and no prebuilt file).  A failed build is
+    reported and tolerated: the GPU cross-check that uses it is skipped, nothing else depends on it."""
+    ref_root = os.environ.get("NSV_REFERENCE_ROOT", "/root/reference")
+    script = os.path.join(HERE, "build_ref_gpu.sh")
+    if os.path.isdir(ref_root) and (force or _stale(REF_GPU_SO, [script])):
+        try:
+            subprocess.check_call(["bash", script])
+        except subprocess.CalledProcessError as e:
+            print(f"oracle.build: reference CUDA extension not built ({e}); its GPU cross-check will be skipped")
+    return REF_GPU_SO if os.path.exists(REF_GPU_SO) else None
+
+
 if __name__ == "__main__":
     print(build_oracle(force=True))
     print(build_ref(force=True))
+    print(build_ref_gpu(force=True))

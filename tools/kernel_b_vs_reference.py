@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""Kernel B against the reference's OWN CUDA extension on the same GPU (test infrastructure + baseline timing).
+
+oracle/build_ref_gpu.sh compiles nesvor/slice_acquisition/slice_acq_cuda.cpp + slice_acq_cuda_kernel.cu for sm_100a
+from where they lie under /root/reference (one-token torch-2.x fix applied in a scratch copy) into
+oracle/_ref/nesvor_ref_slice_acq_cuda.so, which travels to the GPU box.  This script
+
+  * runs all four operators (forward, backward, adjoint forward with / without `equalize`, adjoint backward) of both
+    implementations on identical seeded inputs, with and without masks, and reports relative L2 differences;
+  * with --reps > 0 times the forward / adjoint operators of both on the BASELINE config-2 stack simulation (231 slices
+    of 225^2 pixels, 128^3 volume, PSF of ratio (1, 1, 3)), CUDA events, L2 flushed between launches.
+
+Prints ONE JSON line; {"available": false, "why": ...} when the extension is absent or unusable.  It is run as a
+subprocess by tests/test_gpu_slice_acq.py and bench.py so that foreign kernels cannot touch their CUDA contexts.
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=5)
+    a = ap.parse_args()
+    import torch
+
+    from oracle import ref_gpu
+
+    ref = ref_gpu.load()
+    if ref is None or not torch.cuda.is_available():
+        print(json.dumps({"available": False, "why": ref_gpu.why_not() or "no CUDA device"}))
+        return
+    import importlib
+
+    from helpers import cuda, slice_acq_case
+
+    sa = importlib.import_module("nesvor_b200.slice_acquisition.slice_acq")
+    empty = torch.empty(0, device="cuda")
+    out = {"available": True, "rel_l2": {}}
+    for masks in (False, True):
+        c = slice_acq_case(seed=5, masks=masks, D=40, H=44, W=48, n=9, h=36, w=34)
+        tf, vol, psf = cuda(c["transforms"]), cuda(c["vol"]), cuda(c["psf"])
+        vm, sm = (cuda(c["vol_mask"]), cuda(c["slices_mask"])) if masks else (empty, empty)
+        ovm, osm = (vm, sm) if masks else (None, None)
+        slices, gs, gv = cuda(c["slices"]), cuda(c["grad_slices"]), cuda(c["grad_vol"])
+        res = float(c["res_slice"])
+        r, o = {}, {}
+        r["slices"], r["weight"] = ref.forward(tf, vol, vm, sm, psf, list(c["slice_shape"]), res, True, False)
+        o["slices"], o["weight"] = sa.forward(tf, vol, ovm, osm, psf, c["slice_shape"], res, True, False)
+        r["bwd_grad_vol"], r["bwd_grad_tf"] = ref.backward(tf, vol, vm, psf, gs, sm, res, False, True, True)
+        o["bwd_grad_vol"], o["bwd_grad_tf"] = sa.backward(tf, vol, ovm, psf, gs, osm, res, False, True, True)
+        for eq in (0, 1):
+            ro = ref.adjoint_forward(tf, psf, slices, sm, vm, list(c["vol_shape"]), res, False, bool(eq))
+            ov, ovw = sa.adjoint_forward(tf, psf, slices, osm, ovm, c["vol_shape"], res, False, eq)
+            r[f"adj{eq}_vol"], o[f"adj{eq}_vol"] = ro[0], ov
+            rvw = ro[1] if eq else empty
+            r[f"adjbwd{eq}_grad_slices"], r[f"adjbwd{eq}_grad_tf"] = ref.adjoint_backward(
+                tf, gv.clone(), rvw, vm, psf, slices, sm, ro[0] if eq else empty, res, False, bool(eq), True, True)
+            o[f"adjbwd{eq}_grad_slices"], o[f"adjbwd{eq}_grad_tf"] = sa.adjoint_backward(
+                tf, gv.clone(), ovw, ovm, psf, slices, osm, ov, res, False, eq, True, True)
+        torch.cuda.synchronize()
+        out["rel_l2"]["masked" if masks else "plain"] = {k: rel_l2(o[k], r[k]) for k in r}
+    if a.reps > 0:
+        from nesvor_b200.data.phantom import STACK_ORIENTATIONS, phantom3d, stack_axisangles, stack_geometry
+        from nesvor_b200.transform import RigidTransform, mat_update_resolution
+        from nesvor_b200.utils import get_PSF
+
+        dev = torch.device("cuda", 0)
+        n = 128
+        ss, n_slice = stack_geometry(n, 1.0, 1.0, 3.0)
+        vol = torch.tensor(phantom3d(n), dtype=torch.float32, device=dev)[None, None]
+        psf = get_PSF(res_ratio=(1.0, 1.0, 3.0), device=dev)
+        ax = stack_axisangles(STACK_ORIENTATIONS[:3], n_slice, 3.0).to(dev)
+        mat = mat_update_resolution(RigidTransform(ax, trans_first=True).matrix(), 1, 1.0).contiguous()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def timed(fn):
+            durs = []
+            for i in range(1 + a.reps):
+                flush.zero_()
+                k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                k0.record()
+                res_ = fn()
+                k1.record()
+                torch.cuda.synchronize()
+                if i >= 1:
+                    durs.append(k0.elapsed_time(k1))
+            return res_, sum(durs) / len(durs)
+
+        s_ref, t_ref_f = timed(lambda: ref.forward(mat, vol, empty, empty, psf, [ss, ss], 1.0, False, False)[0])
+        s_our, t_our_f = timed(lambda: sa.forward(mat, vol, None, None, psf, (ss, ss), 1.0, False, False)[0])
+        _, t_ref_a = timed(lambda: ref.adjoint_forward(mat, psf, s_ref, empty, empty, [n, n, n], 1.0, False, False)[0])
+        _, t_our_a = timed(lambda: sa.adjoint_forward(mat, psf, s_our, None, None, (n, n, n), 1.0, False, False)[0])
+        out["config2_stack_simulation_ms"] = {"slices": int(s_ref.shape[0]), "slice_shape": [ss, ss], "psf_taps": int((psf != 0).sum()),
+                                              "forward": {"reference_cuda_extension": t_ref_f, "nesvor_b200": t_our_f},
+                                              "adjoint_forward": {"reference_cuda_extension": t_ref_a, "nesvor_b200": t_our_a},
+                                              "forward_rel_l2": rel_l2(s_our, s_ref)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
