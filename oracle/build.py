@@ -40,12 +40,13 @@ REF_GPU_SO = os.path.join(HERE, "_ref", "nesvor_ref_slice_acq_cuda.so")
 
 
 def build_ref_gpu(force=False):
-    """The reference's own slice-acquisition CUDA extension for sm_100a (oracle/build_ref_gpu.sh, ~3 min with torch
-    headers); returns its path, or None when it cannot exist (no /root/reference and no prebuilt file).  A failed build is
+    """The reference's own CUDA extensions (slice acquisition, pose converters) for sm_100a (oracle/build_ref_gpu.sh, ~3 min
+    each with torch headers); returns the slice-acquisition module's path, or None when it cannot exist (no /root/reference and no prebuilt file).  A failed build is
     reported and tolerated: the GPU cross-check that uses it is skipped, nothing else depends on it."""
     ref_root = os.environ.get("NSV_REFERENCE_ROOT", "/root/reference")
     script = os.path.join(HERE, "build_ref_gpu.sh")
-    if os.path.isdir(ref_root) and (force or _stale(REF_GPU_SO, [script])):
+    both = [REF_GPU_SO, os.path.join(HERE, "_ref", "nesvor_ref_transform_convert_cuda.so")]
+    if os.path.isdir(ref_root) and (force or any(_stale(so, [script]) for so in both)):
         try:
             subprocess.check_call(["bash", script])
         except subprocess.CalledProcessError as e:

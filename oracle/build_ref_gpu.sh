@@ -1,25 +1,23 @@
 #!/usr/bin/env bash
 # TEST INFRASTRUCTURE ONLY.
-# Builds the reference's OWN slice-acquisition CUDA extension for sm_100a, straight from where its two source files lie
-# under /root/reference, into oracle/_ref/nesvor_ref_slice_acq_cuda.so (git-ignored, travels with gpurun) -- the GPU-side
-# cross-check / baseline for kernel B.  It does not run the reference's build system
-# (setup.py / torch JIT): g++ for slice_acq_cuda.cpp, nvcc for slice_acq_cuda_kernel.cu.  The .cu file does not compile
-# against torch 2.11 as shipped (6 x AT_DISPATCH_FLOATING_TYPES(x.type(), ...)); the one-token fix
+# Builds the reference's OWN CUDA extensions for sm_100a -- slice acquisition and the pose converters -- straight from
+# where their source files lie under /root/reference, into oracle/_ref/nesvor_ref_slice_acq_cuda.so and
+# oracle/_ref/nesvor_ref_transform_convert_cuda.so (git-ignored, travel with gpurun): the GPU-side cross-check / baseline
+# for kernel B and the converters.  It does not run the reference's build system
+# (setup.py / torch JIT): g++ for the *_cuda.cpp bindings, nvcc for the *_cuda_kernel.cu files.  The .cu files do not compile
+# against torch 2.11 as shipped (10 x AT_DISPATCH_FLOATING_TYPES(x.type(), ...)); the one-token fix
 # (.type() -> .scalar_type()) is applied with sed into a scratch file under $TMPDIR that is deleted afterwards --
 # nothing from /root/reference is copied into the repository.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 REF="${NSV_REFERENCE_ROOT:-/root/reference}"
-CPP="$REF/nesvor/slice_acquisition/slice_acq_cuda.cpp"
-CU="$REF/nesvor/slice_acquisition/slice_acq_cuda_kernel.cu"
-OUT="$HERE/_ref/nesvor_ref_slice_acq_cuda.so"
-if [[ ! -f "$CPP" || ! -f "$CU" ]]; then
-  echo "build_ref_gpu.sh: reference sources not found under $REF -- skipping (a prebuilt $OUT is used if present)" >&2
-  exit 0
-fi
 PY="${NSV_PYTHON:-python}"
 NVCC="${NSV_NVCC:-/usr/local/cuda/bin/nvcc}"
 CXX="${NSV_CXX:-/usr/bin/g++}"
+if [[ ! -f "$REF/nesvor/slice_acquisition/slice_acq_cuda.cpp" || ! -f "$REF/nesvor/transform/transform_convert_cuda.cpp" ]]; then
+  echo "build_ref_gpu.sh: reference sources not found under $REF -- skipping (prebuilt files under $HERE/_ref are used if present)" >&2
+  exit 0
+fi
 mkdir -p "$HERE/_ref"
 SCRATCH="$(mktemp -d)"
 trap 'rm -rf "$SCRATCH"' EXIT
@@ -33,12 +31,24 @@ PYEOF
 IFLAGS=""
 IFS=',' read -ra ARR <<<"$INCS"
 for i in "${ARR[@]}"; do IFLAGS="$IFLAGS -isystem $i"; done
-DEFS="-DTORCH_EXTENSION_NAME=nesvor_ref_slice_acq_cuda -DTORCH_API_INCLUDE_EXTENSION_H -D_GLIBCXX_USE_CXX11_ABI=1"
-sed -E 's/AT_DISPATCH_FLOATING_TYPES\(([A-Za-z_]+)\.type\(\)/AT_DISPATCH_FLOATING_TYPES(\1.scalar_type()/' "$CU" > "$SCRATCH/kernel.cu"
-$CXX -O2 -fPIC -std=c++17 -w $DEFS $IFLAGS -c "$CPP" -o "$SCRATCH/binding.o" &
-$NVCC -O3 -std=c++17 -w -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC --expt-relaxed-constexpr $DEFS $IFLAGS \
-  -c "$SCRATCH/kernel.cu" -o "$SCRATCH/kernel.o"
-wait
-$CXX -shared -o "$OUT" "$SCRATCH/binding.o" "$SCRATCH/kernel.o" -L"$LIBDIR" -Wl,-rpath,"$LIBDIR" -lc10 -ltorch_cpu -ltorch -ltorch_python \
-  -lc10_cuda -ltorch_cuda -L/usr/local/cuda/lib64 -lcudart
-echo "built $OUT"
+
+# build_one <module name> <binding .cpp> <kernel .cu>
+build_one() {
+  local NAME="$1" CPP="$2" CU="$3" OUT="$HERE/_ref/$1.so"
+  local DEFS="-DTORCH_EXTENSION_NAME=$NAME -DTORCH_API_INCLUDE_EXTENSION_H -D_GLIBCXX_USE_CXX11_ABI=1"
+  sed -E 's/AT_DISPATCH_FLOATING_TYPES\(([A-Za-z_]+)\.type\(\)/AT_DISPATCH_FLOATING_TYPES(\1.scalar_type()/' "$CU" > "$SCRATCH/$NAME.cu"
+  $CXX -O2 -fPIC -std=c++17 -w $DEFS $IFLAGS -c "$CPP" -o "$SCRATCH/$NAME.binding.o" &
+  $NVCC -O3 -std=c++17 -w -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC --expt-relaxed-constexpr $DEFS $IFLAGS \
+    -c "$SCRATCH/$NAME.cu" -o "$SCRATCH/$NAME.kernel.o"
+  wait
+  $CXX -shared -o "$OUT" "$SCRATCH/$NAME.binding.o" "$SCRATCH/$NAME.kernel.o" -L"$LIBDIR" -Wl,-rpath,"$LIBDIR" -lc10 -ltorch_cpu -ltorch \
+    -ltorch_python -lc10_cuda -ltorch_cuda -L/usr/local/cuda/lib64 -lcudart
+  echo "built $OUT"
+}
+WHAT="${1:-all}"
+if [[ "$WHAT" == "all" || "$WHAT" == "slice_acq" ]]; then
+  build_one nesvor_ref_slice_acq_cuda "$REF/nesvor/slice_acquisition/slice_acq_cuda.cpp" "$REF/nesvor/slice_acquisition/slice_acq_cuda_kernel.cu"
+fi
+if [[ "$WHAT" == "all" || "$WHAT" == "transform" ]]; then
+  build_one nesvor_ref_transform_convert_cuda "$REF/nesvor/transform/transform_convert_cuda.cpp" "$REF/nesvor/transform/transform_convert_cuda_kernel.cu"
+fi

