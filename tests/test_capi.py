@@ -115,3 +115,34 @@ def test_bias_mean_and_trans_reg_reject_bad_arguments_without_gpu(native_lib):
     assert native_lib.nsv_trans_reg_f32(None, None, None, None, ctypes.c_int(0), ctypes.c_float(1.0), None) == 0
     assert native_lib.nsv_trans_reg_f32(None, None, None, None, ctypes.c_int(3), ctypes.c_float(1.0), None) == -1
     assert native_lib.nsv_trans_reg_f32(None, None, None, None, ctypes.c_int(-1), ctypes.c_float(1.0), None) == -1
+
+
+def test_reference_cuda_extensions_load_and_accept_the_cross_check_calls():
+    """oracle/_ref/nesvor_ref_{slice_acq,transform_convert}_cuda.so (the reference's own extensions compiled for sm_100a by
+    oracle/build_ref_gpu.sh): importable, sm_100a cubin inside, and every call made by tools/kernel_b_vs_reference.py gets
+    past pybind's argument conversion -- with CPU tensors it must stop at the reference's CHECK_CUDA, not at a TypeError.
+    Skipped when the files were not built (no /root/reference)."""
+    import subprocess
+
+    import torch
+
+    from oracle import ref_gpu
+
+    sa, tc = ref_gpu.load(), ref_gpu.load_transform()
+    if sa is None or tc is None:
+        pytest.skip("reference CUDA extensions not built: " + ref_gpu.why_not())
+    for name in ("nesvor_ref_slice_acq_cuda", "nesvor_ref_transform_convert_cuda"):
+        out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "oracle", "_ref", name + ".so")], capture_output=True, text=True).stdout
+        assert set(re.findall(r"sm_\d+a?", out)) == {"sm_100a"}
+    e = torch.empty(0)
+    tf, vol, psf = torch.zeros(2, 3, 4), torch.zeros(1, 1, 4, 4, 4), torch.ones(3, 3, 3)
+    sl = torch.zeros(2, 1, 5, 5)
+    calls = [lambda: sa.forward(tf, vol, e, e, psf, [5, 5], 1.0, True, False),
+             lambda: sa.backward(tf, vol, e, psf, sl, e, 1.0, False, True, True),
+             lambda: sa.adjoint_forward(tf, psf, sl, e, e, [4, 4, 4], 1.0, False, True),
+             lambda: sa.adjoint_backward(tf, vol, e, e, psf, sl, e, e, 1.0, False, False, True, True),
+             lambda: tc.axisangle2mat_forward(torch.zeros(2, 6)), lambda: tc.axisangle2mat_backward(tf, torch.zeros(2, 6)),
+             lambda: tc.mat2axisangle_forward(tf), lambda: tc.mat2axisangle_backward(tf, torch.zeros(2, 6))]
+    for call in calls:
+        with pytest.raises(RuntimeError, match="is_cuda"):
+            call()
