@@ -58,7 +58,7 @@ def _worker(rank, world, port, out):
     g = _flat_grad(om, shard_batch(batch, rank, world), noise[lo:hi])
     scale = allreduce_gradient(g, dist, world, local_count=hi - lo, global_count=n)
     if rank == 0:
-        out.put((g * scale).clone())
+        out.put((g * scale).numpy().copy())  # by value (a torch tensor would travel as a shared-memory handle of this process)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -77,7 +77,7 @@ def test_two_rank_gradient_equals_single_process():
         assert p.exitcode == 0
     om, batch, noise = _make()
     ref = _flat_grad(om, batch, noise)
-    torch.testing.assert_close(got, ref, rtol=1e-9, atol=1e-12)
+    torch.testing.assert_close(torch.from_numpy(got), ref, rtol=1e-9, atol=1e-12)
 
 
 def test_shard_bounds_cover_everything():
@@ -120,7 +120,7 @@ def _bias_worker(rank, world, port, out):
     g = torch.cat([(om.P[k].grad if om.P[k].grad is not None else torch.zeros_like(om.P[k])).reshape(-1) for k in om.trainable])
     scale = allreduce_gradient(g, dist, world, local_count=hi - lo, global_count=n)
     if rank == 0:
-        out.put(((g * scale).clone(), float(m)))
+        out.put(((g * scale).numpy().copy(), float(m)))  # by value: a torch tensor travels as a shared-memory handle that dies with the sender
     dist.barrier()
     dist.destroy_process_group()
 
@@ -179,7 +179,7 @@ def test_two_rank_bias_head_gradient_equals_single_process():
     (losses["MSE"] + losses["logVar"] + om.cfg.weight_bias * losses["biasReg"]).backward()
     g_ref = torch.cat([(om.P[k].grad if om.P[k].grad is not None else torch.zeros_like(om.P[k])).reshape(-1) for k in om.trainable])
     assert abs(mean_dp**2 - float(losses["biasReg"].detach())) < 1e-12
-    torch.testing.assert_close(g_dp, g_ref, rtol=1e-9, atol=1e-12)
+    torch.testing.assert_close(torch.from_numpy(g_dp), g_ref, rtol=1e-9, atol=1e-12)
 
 
 def _dataset_worker(rank, world, port, out):
@@ -201,7 +201,7 @@ def _dataset_worker(rank, world, port, out):
     for _ in range(7):  # 16-pixel batches from a 50-pixel table: crosses two epoch boundaries
         b = ds.get_batch(16, torch.device("cpu"))
         assert torch.equal(b["xyz"][:, 0] / 3, b["v"]) and torch.equal(b["slice_idx"], b["v"].long() % 7)  # rows stay together
-        seen.append((b["v"].clone(), shard_batch(b, rank, world)["v"].clone()))
+        seen.append((b["v"].tolist(), shard_batch(b, rank, world)["v"].tolist()))  # plain lists: pickled by value
     out.put((rank, seen, ds.epoch))
     dist.barrier()
     dist.destroy_process_group()
@@ -223,7 +223,7 @@ def test_dataset_batches_are_identical_across_ranks_and_sharded_disjointly():
         assert p.exitcode == 0
     assert res[0][1] == res[1][1] == 3
     for (g0, s0), (g1, s1) in zip(res[0][0], res[1][0]):
-        assert torch.equal(g0, g1)  # the same global batch on both ranks
-        assert torch.equal(torch.cat([s0, s1]), g0)  # rank chunks tile it
-    first_epoch = torch.cat([g for g, _ in res[0][0][:3]])
-    assert first_epoch.unique().numel() == 48  # 3 batches of one permutation: no repeats
+        assert g0 == g1  # the same global batch on both ranks
+        assert s0 + s1 == g0  # rank chunks tile it
+    first_epoch = [x for g, _ in res[0][0][:3] for x in g]
+    assert len(set(first_epoch)) == 48  # 3 batches of one permutation: no repeats
