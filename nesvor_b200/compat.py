@@ -29,11 +29,22 @@ import torch
 _NAMES = ("nesvor.slice_acq_cuda", "nesvor.transform_convert_cuda", "tinycudann")
 
 
+def _lenient(fn):
+    """The pybind modules insist on contiguous tensors (CHECK_CONTIGUOUS) and the reference's converter Functions hand
+    autograd's gradients over as they come; newer torch versions produce expanded / strided gradients in places where the
+    torch the reference was written for did not, so the stand-ins make tensor arguments contiguous instead of raising."""
+    def call(*args):
+        return fn(*[a.contiguous() if isinstance(a, torch.Tensor) and a.numel() and not a.is_contiguous() else a for a in args])
+
+    call.__name__, call.__doc__, call.__module__ = fn.__name__, fn.__doc__, fn.__module__
+    return call
+
+
 def _slice_acq_module() -> types.ModuleType:
     sa = importlib.import_module("nesvor_b200.slice_acquisition.slice_acq")
     m = types.ModuleType("nesvor.slice_acq_cuda", "nesvor_b200 stand-in for the reference's slice_acq_cuda pybind module")
     for fn in ("forward", "backward", "adjoint_forward", "adjoint_backward"):
-        setattr(m, fn, getattr(sa, fn))
+        setattr(m, fn, _lenient(getattr(sa, fn)))
     return m
 
 
@@ -41,7 +52,7 @@ def _transform_convert_module() -> types.ModuleType:
     tc = importlib.import_module("nesvor_b200.transform.transform_convert")
     m = types.ModuleType("nesvor.transform_convert_cuda", "nesvor_b200 stand-in for the reference's transform_convert_cuda pybind module")
     for fn in ("axisangle2mat_forward", "axisangle2mat_backward", "mat2axisangle_forward", "mat2axisangle_backward"):
-        setattr(m, fn, getattr(tc, fn))
+        setattr(m, fn, _lenient(getattr(tc, fn)))
     return m
 
 

@@ -54,7 +54,27 @@ def build_ref_gpu(force=False):
     return REF_GPU_SO if os.path.exists(REF_GPU_SO) else None
 
 
+REF_PKG = os.path.join(os.path.dirname(HERE), "baseline", "_ref", "nesvor")
+
+
+def install_reference_package(force=False):
+    """The UNMODIFIED pure-Python layer of the reference (every nesvor/**/*.py, nothing else) placed under the git-ignored
+    baseline/_ref/ so that it travels to the GPU box, where tests run the reference's own INR / NeSVoR on this library
+    through nesvor_b200.compat (its three native imports).  `pip install --target baseline/_ref /root/reference` cannot be
+    used: setup.py builds the two CUDA extensions, which do not compile against torch 2.11 as shipped, and
+    the hot path imports tinycudann.  Returns the package path or None."""
+    import shutil
+
+    src = os.path.join(os.environ.get("NSV_REFERENCE_ROOT", "/root/reference"), "nesvor")
+    if os.path.isdir(src) and (force or not os.path.isdir(REF_PKG)):
+        if os.path.isdir(REF_PKG):
+            shutil.rmtree(REF_PKG)
+        shutil.copytree(src, REF_PKG, ignore=lambda d, names: [n for n in names if not (n.endswith(".py") or os.path.isdir(os.path.join(d, n)))])
+    return REF_PKG if os.path.isdir(REF_PKG) else None
+
+
 if __name__ == "__main__":
     print(build_oracle(force=True))
     print(build_ref(force=True))
     print(build_ref_gpu(force=True))
+    print(install_reference_package(force=True))
