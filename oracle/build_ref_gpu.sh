@@ -46,9 +46,13 @@ build_one() {
   echo "built $OUT"
 }
 WHAT="${1:-all}"
+PIDS=()
 if [[ "$WHAT" == "all" || "$WHAT" == "slice_acq" ]]; then
-  build_one nesvor_ref_slice_acq_cuda "$REF/nesvor/slice_acquisition/slice_acq_cuda.cpp" "$REF/nesvor/slice_acquisition/slice_acq_cuda_kernel.cu"
+  ( build_one nesvor_ref_slice_acq_cuda "$REF/nesvor/slice_acquisition/slice_acq_cuda.cpp" "$REF/nesvor/slice_acquisition/slice_acq_cuda_kernel.cu" ) &
+  PIDS+=($!)
 fi
 if [[ "$WHAT" == "all" || "$WHAT" == "transform" ]]; then
-  build_one nesvor_ref_transform_convert_cuda "$REF/nesvor/transform/transform_convert_cuda.cpp" "$REF/nesvor/transform/transform_convert_cuda_kernel.cu"
+  ( build_one nesvor_ref_transform_convert_cuda "$REF/nesvor/transform/transform_convert_cuda.cpp" "$REF/nesvor/transform/transform_convert_cuda_kernel.cu" ) &
+  PIDS+=($!)
 fi
+for p in "${PIDS[@]}"; do wait "$p"; done   # the two extensions build side by side; any failure fails the script (set -e)
