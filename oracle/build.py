@@ -55,21 +55,25 @@ def build_ref_gpu(force=False):
 
 
 REF_PKG = os.path.join(os.path.dirname(HERE), "baseline", "_ref", "nesvor")
+REF_TESTS = os.path.join(os.path.dirname(HERE), "baseline", "_ref", "tests")
 
 
 def install_reference_package(force=False):
     """The UNMODIFIED pure-Python layer of the reference (every nesvor/**/*.py, nothing else) placed under the git-ignored
     baseline/_ref/ so that it travels to the GPU box, where tests run the reference's own INR / NeSVoR on this library
-    through nesvor_b200.compat (its three native imports).  `pip install --target baseline/_ref /root/reference` cannot be
+    through nesvor_b200.compat (its three native imports), and the reference's own unit tests (tests/**/*.py) next to it.  `pip install --target baseline/_ref /root/reference` cannot be
     used: setup.py builds the two CUDA extensions, which do not compile against torch 2.11 as shipped, and
     the hot path imports tinycudann.  Returns the package path or None."""
     import shutil
 
-    src = os.path.join(os.environ.get("NSV_REFERENCE_ROOT", "/root/reference"), "nesvor")
-    if os.path.isdir(src) and (force or not os.path.isdir(REF_PKG)):
-        if os.path.isdir(REF_PKG):
-            shutil.rmtree(REF_PKG)
-        shutil.copytree(src, REF_PKG, ignore=lambda d, names: [n for n in names if not (n.endswith(".py") or os.path.isdir(os.path.join(d, n)))])
+    ref_root = os.environ.get("NSV_REFERENCE_ROOT", "/root/reference")
+    only_py = lambda d, names: [n for n in names if not (n.endswith(".py") or os.path.isdir(os.path.join(d, n)))]  # noqa: E731
+    for sub, dst in (("nesvor", REF_PKG), ("tests", REF_TESTS)):  # the package and the reference's own unit tests
+        src = os.path.join(ref_root, sub)
+        if os.path.isdir(src) and (force or not os.path.isdir(dst)):
+            if os.path.isdir(dst):
+                shutil.rmtree(dst)
+            shutil.copytree(src, dst, ignore=only_py)
     return REF_PKG if os.path.isdir(REF_PKG) else None
 
 

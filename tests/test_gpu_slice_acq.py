@@ -170,33 +170,3 @@ def test_adjointness_at_baseline_size(native_lib):
     lhs, rhs = float((Ax * y).sum()), float((x * Aty).sum())
     assert interior.float().mean() > 0.05
     np.testing.assert_allclose(lhs, rhs, rtol=1e-9)
-
-
-def test_against_reference_cuda_extension_on_the_gpu(native_lib):
-    """Kernel B vs the reference's OWN CUDA extension compiled for sm_100a (oracle/build_ref_gpu.sh: slice_acq_cuda.cpp +
-    slice_acq_cuda_kernel.cu from /root/reference with the one-token torch-2.x fix), same inputs, same GPU, all four
-    operators, with and without masks (tools/kernel_b_vs_reference.py, run in a subprocess so that a foreign kernel can
-    never poison this process's CUDA context).  The reference kernels are compiled with FMA contraction and scatter with
-    atomics, ours reproduce the un-contracted CPU arithmetic (-fmad=false): agreement is at fp32 round-off -- relative L2
-    <= 1e-5 for the gathers, 1e-4 for the scatter passes, 1e-3 for the pose gradients.  Skipped when the prebuilt
-    extension is absent or cannot be loaded / called on this box."""
-    import json
-    import subprocess
-    import sys
-
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "kernel_b_vs_reference.py"), "--reps", "0"], capture_output=True, text=True, timeout=600)
-    line = next((l for l in reversed(r.stdout.splitlines()) if l.startswith("{")), None)
-    if r.returncode != 0 or line is None:
-        pytest.skip("reference CUDA extension check did not run here: " + (r.stderr or r.stdout)[-300:])
-    out = json.loads(line)
-    if not out.get("available"):
-        pytest.skip("reference CUDA extension not available: " + str(out.get("why")))
-    print(line)
-    for case, errs in out["rel_l2"].items():
-        for k, err in errs.items():
-            if case == "pose_converters":  # same formulas, FMA-contracted vs literal arithmetic; the backward passes divide by sin / theta
-                assert err <= (1e-5 if k.endswith("fwd") else 1e-3), (case, k, err)
-                continue
-            tol = 1e-3 if k.endswith("grad_tf") else (1e-5 if k in ("slices", "weight") or k.endswith("adjbwd0_grad_slices") else 1e-4)
-            assert err <= tol, (case, k, err)

@@ -12,7 +12,7 @@ oracle/_ref/nesvor_ref_slice_acq_cuda.so, which travels to the GPU box.  This sc
     of 225^2 pixels, 128^3 volume, PSF of ratio (1, 1, 3)), CUDA events, L2 flushed between launches.
 
 Prints ONE JSON line; {"available": false, "why": ...} when the extension is absent or unusable.  It is run as a
-subprocess by tests/test_gpu_slice_acq.py and bench.py so that foreign kernels cannot touch their CUDA contexts.
+subprocess by tests/test_gpu_zz_reference.py and bench.py so that foreign kernels cannot touch their CUDA contexts.
 """
 import argparse
 import json

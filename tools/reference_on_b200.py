@@ -15,7 +15,7 @@ parameters of this package's mirror, and on the same batch (same torch RNG state
     kernels" figure.
 
 Prints ONE JSON line ({"available": false, "why": ...} if the reference copy is absent).  Run as a subprocess by
-tests/test_gpu_e2e.py so that nothing of the reference package enters the test process.
+tests/test_gpu_zz_reference.py so that nothing of the reference package enters the test process.
 """
 import json
 import os

@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Runs the REFERENCE's OWN unit tests for the path, unmodified, on libnesvor_b200 (GPU box).
+
+baseline/_ref holds `nesvor/**/*.py` and `tests/**/*.py` exactly as they lie under /root/reference (copied by
+oracle.build.install_reference_package; git-ignored, travels with gpurun).  With nesvor_b200.compat supplying the three
+native imports, the reference's unittest modules that touch native code are executed as they are:
+
+  tests.transform.test_transform_convert   axisangle2mat / mat2axisangle vs scipy on the 11 hand-picked vectors (+ the
+                                           reference's pure-torch point / Euler converters)
+  tests.transform.test_transform           compose / inv identity through RigidTransform
+  tests.slice_acquisition.test_slice_acq   CG-SRR (the reference's svort/srr.py) recovers phantom(32) through A / A^T, atol 3e-5
+
+(tests.svort.test_cg exercises only the reference's pure-torch CG against scipy and calls scipy.sparse.linalg.cg with the
+`tol=` keyword that scipy >= 1.14 removed; tests.image / test_vvr need nibabel / the SVoRT registration: not run.)
+Prints ONE JSON line: {"available", "tests_run", "failures", "errors", "skipped", "details"}.
+"""
+import io
+import json
+import os
+import sys
+import types
+import unittest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_PARENT = os.path.join(ROOT, "baseline", "_ref")
+MODULES = ["tests.transform.test_transform_convert", "tests.transform.test_transform", "tests.slice_acquisition.test_slice_acq"]
+
+
+def main():
+    import torch
+
+    if not os.path.isdir(os.path.join(REF_PARENT, "tests")) or not os.path.isdir(os.path.join(REF_PARENT, "nesvor")):
+        print(json.dumps({"available": False, "why": "baseline/_ref/{nesvor,tests} absent"}))
+        return
+    if not torch.cuda.is_available():
+        print(json.dumps({"available": False, "why": "no CUDA device"}))
+        return
+    sys.path.insert(0, ROOT)
+    import nesvor_b200.compat as compat
+
+    compat.install()
+    sys.path.insert(0, REF_PARENT)  # `import nesvor`, `import tests` now resolve to the reference's copies
+    os.chdir(REF_PARENT)
+    try:
+        import nibabel  # noqa: F401
+    except ImportError:
+        sys.modules["nibabel"] = types.ModuleType("nibabel")
+    suite = unittest.defaultTestLoader.loadTestsFromNames(MODULES)
+    stream = io.StringIO()
+    res = unittest.TextTestRunner(stream=stream, verbosity=2).run(suite)
+    details = [f"{kind}: {test.id()}: {tb.strip().splitlines()[-1][:200]}" for kind, lst in (("FAIL", res.failures), ("ERROR", res.errors)) for test, tb in lst]
+    import nesvor.slice_acquisition.slice_acq as rsa
+
+    print(json.dumps({"available": True, "tests_run": res.testsRun, "failures": len(res.failures), "errors": len(res.errors),
+                      "skipped": len(res.skipped), "details": details, "native_module": rsa.slice_acq_cuda.__doc__,
+                      "log_tail": stream.getvalue().strip().splitlines()[-12:]}))
+
+
+if __name__ == "__main__":
+    main()
