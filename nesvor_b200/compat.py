@@ -1,12 +1,14 @@
 """Zero-edit drop-in: run the UNMODIFIED reference package (daviddmc/NeSVoR) on libnesvor_b200.
 
-The reference reaches native code through exactly three imports:
+The reference reaches native code (and, for files, one third-party package) through these imports:
 
 * `import nesvor.slice_acq_cuda`          (nesvor/slice_acquisition/slice_acq.py:5-19; else it JIT-compiles its .cu files)
 * `import nesvor.transform_convert_cuda`  (nesvor/transform/transform_convert.py:3-18; same fallback)
 * `import tinycudann as tcnn`             (nesvor/nesvor/models.py:7; `tcnn.Encoding` :25, `tcnn.Network` :31)
 
-`install()` registers modules under those three names whose functions / classes have the pybind / tcnn signatures and
+* `import nibabel as nib`                 (nesvor/image/image.py:5; `nib.load`, `nib.nifti1.Nifti1Image`, `nib.save` only)
+
+`install()` registers modules under those names whose functions / classes have the pybind / tcnn signatures and
 call the C ABI (include/nesvor_b200.h) -- `forward / backward / adjoint_forward / adjoint_backward`,
 `axisangle2mat_{forward,backward} / mat2axisangle_{forward,backward}` (each returning a list of tensors, absent masks as
 empty tensors, like slice_acq_cuda.cpp:61-161 and transform_convert_cuda.cpp:27-69), `Encoding(n_input_dims,
@@ -17,7 +19,8 @@ encoding_config, dtype)` and `Network(n_input_dims, n_output_dims, network_confi
 
 the reference's own `INR`, `NeSVoR`, `train`, `slice_acquisition`, `RigidTransform`, SRR ... run on the B200 kernels
 (the unfused path: one native op per reference op; the fused iteration is `nesvor_b200.train(..., args.fused=True)`).
-A real `tinycudann`, if installed, is left alone unless `tcnn="force"`.
+A real `tinycudann` / `nibabel`, if installed, is left alone unless `tcnn="force"` / `nibabel="force"`; the nibabel stand-in
+covers single-file NIfTI-1 (`image/nifti.py`).
 """
 import importlib
 import importlib.util
@@ -26,7 +29,7 @@ import types
 
 import torch
 
-_NAMES = ("nesvor.slice_acq_cuda", "nesvor.transform_convert_cuda", "tinycudann")
+_NAMES = ("nesvor.slice_acq_cuda", "nesvor.transform_convert_cuda", "tinycudann", "nibabel", "nibabel.nifti1")
 
 
 def _lenient(fn):
@@ -77,19 +80,76 @@ def _tcnn_module() -> types.ModuleType:
     return m
 
 
-def install(tcnn: str = "auto") -> dict:
-    """Registers the three stand-in modules in `sys.modules`; returns {name: module} of what was installed.
-    tcnn = "auto": only when no real `tinycudann` is importable; "force": always; "never": leave `tinycudann` alone."""
+def _nibabel_module() -> types.ModuleType:
+    """The three nibabel calls the reference makes (nesvor/image/image.py:253-296) on image/nifti.py:
+    `nib.load(path)` -> object with `.header["dim" | "pixdim"]`, `.get_fdata()`, `.affine`, `.get_qform()`;
+    `nib.nifti1.Nifti1Image(data, affine)` with `.header.set_xyzt_units / set_qform / set_sform`; `nib.save(img, path)`."""
+    import numpy as np
+
+    from .image.nifti import read_nifti, write_nifti
+
+    class _Header(dict):
+        def set_xyzt_units(self, *a, **k):  # written files always carry millimetres
+            pass
+
+        def set_qform(self, affine, code=None):  # written files carry the affine as qform "aligned" ...
+            self["_affine"] = np.asarray(affine, np.float64)
+
+        def set_sform(self, affine, code=None):  # ... and as sform "scanner"
+            self["_affine"] = np.asarray(affine, np.float64)
+
+    class Nifti1Image:
+        def __init__(self, dataobj, affine, header=None):
+            self._data = np.asarray(dataobj)
+            self.affine = np.eye(4) if affine is None else np.asarray(affine, np.float64)
+            self.header = _Header(header or {})
+            self._qform = None
+
+        def get_fdata(self):
+            return np.asarray(self._data, np.float64)
+
+        def get_qform(self):
+            return self.affine if self._qform is None else self._qform
+
+    def load(path):
+        data, hdr = read_nifti(str(path))
+        img = Nifti1Image(data, hdr["affine"], {"dim": hdr["dim"], "pixdim": hdr["pixdim"].astype(np.float32)})
+        img._qform = hdr["qform"]
+        return img
+
+    def save(img, path):
+        write_nifti(str(path), img._data, img.header.get("_affine", img.affine))
+
+    m = types.ModuleType("nibabel", "nesvor_b200 stand-in for the three nibabel calls NeSVoR makes (NIfTI-1 single files)")
+    n1 = types.ModuleType("nibabel.nifti1")
+    n1.Nifti1Image = Nifti1Image
+    m.nifti1, m.Nifti1Image, m.load, m.save = n1, Nifti1Image, load, save
+    m.__nesvor_b200_shim__ = n1.__nesvor_b200_shim__ = True
+    return m
+
+
+def _have_real(name: str) -> bool:
+    cur = sys.modules.get(name)
+    if cur is not None:
+        return not getattr(cur, "__nesvor_b200_shim__", False)
+    try:
+        return importlib.util.find_spec(name) is not None
+    except (ImportError, ValueError):
+        return False
+
+
+def install(tcnn: str = "auto", nibabel: str = "auto") -> dict:
+    """Registers the stand-in modules in `sys.modules`; returns {name: module} of what was installed.
+    tcnn / nibabel = "auto": only when no real `tinycudann` / `nibabel` is importable; "force": always; "never": leave it alone."""
     done = {}
     for name, make in (("nesvor.slice_acq_cuda", _slice_acq_module), ("nesvor.transform_convert_cuda", _transform_convert_module)):
         sys.modules[name] = done[name] = make()
-    have_real = False
-    if tcnn == "auto":
-        cur = sys.modules.get("tinycudann")
-        have_real = (cur is not None and not getattr(cur, "__nesvor_b200_shim__", False)) or (
-            cur is None and importlib.util.find_spec("tinycudann") is not None)
-    if tcnn == "force" or (tcnn == "auto" and not have_real):
+    if tcnn == "force" or (tcnn == "auto" and not _have_real("tinycudann")):
         sys.modules["tinycudann"] = done["tinycudann"] = _tcnn_module()
+    if nibabel == "force" or (nibabel == "auto" and not _have_real("nibabel")):
+        nib = _nibabel_module()
+        sys.modules["nibabel"], sys.modules["nibabel.nifti1"] = nib, nib.nifti1
+        done["nibabel"] = nib
     parent = sys.modules.get("nesvor")  # `import nesvor.x as y` resolves through the parent's attribute first
     if parent is not None:
         for name in ("slice_acq_cuda", "transform_convert_cuda"):
@@ -100,5 +160,5 @@ def install(tcnn: str = "auto") -> dict:
 def uninstall() -> None:
     for name in _NAMES:
         mod = sys.modules.get(name)
-        if mod is not None and (name != "tinycudann" or getattr(mod, "__nesvor_b200_shim__", False)):
+        if mod is not None and (not name.startswith(("tinycudann", "nibabel")) or getattr(mod, "__nesvor_b200_shim__", False)):
             del sys.modules[name]

@@ -17,13 +17,8 @@ from argparse import Namespace
 import torch
 sys.path.insert(0, ROOT)
 sys.path.insert(0, REF)
-if "nibabel" not in sys.modules:
-    try:
-        import nibabel  # noqa: F401
-    except ImportError:
-        sys.modules["nibabel"] = types.ModuleType("nibabel")  # only nesvor/image needs it, at import time
 import nesvor_b200.compat as compat
-installed = compat.install()
+installed = compat.install()                         # nibabel is absent in this image: its stand-in is installed too
 import nesvor                                        # the reference package, as it lies under /root/reference
 import nesvor.slice_acquisition.slice_acq as rsa
 import nesvor.transform.transform_convert as rtc
@@ -62,6 +57,32 @@ for name, call in (("axisangle2mat", lambda: rtc.axisangle2mat(ax)),
         errs[name] = str(e)[:60]
 out["errors"] = errs
 out["train_uses_ref_models"] = rtrain.NeSVoR is rm.NeSVoR
+# ---- the reference's own image module on the nibabel stand-in: write with the reference, read with both
+import os, tempfile
+import numpy as np
+import nesvor.image as rim
+import nesvor_b200.image as oim
+import nesvor.cli.main  # noqa: F401  the whole CLI imports
+rng = np.random.default_rng(0)
+q, r = np.linalg.qr(rng.normal(size=(3, 3)))
+q = q * np.sign(np.diag(r))
+if np.linalg.det(q) < 0:
+    q[:, 2] = -q[:, 2]
+mat = torch.tensor(np.concatenate([q, rng.uniform(-20, 20, (3, 1))], -1)[None], dtype=torch.float32)
+img = torch.tensor(rng.uniform(0.1, 1, (4, 5, 6)), dtype=torch.float32)
+tmp = tempfile.mkdtemp()
+path = os.path.join(tmp, "v.nii.gz")
+rim.Volume(img, img > 0.5, RigidTransform(mat), 0.9, 1.1, 3.0).save(path, masked=False)
+a, b = rim.load_stack(path), oim.load_stack(path)
+out["nifti"] = {"shim": bool(getattr(sys.modules["nibabel"], "__nesvor_b200_shim__", False)), "slices_equal": bool(torch.equal(a.slices, b.slices)),
+                "image_survives": bool(torch.equal(a.slices[:, 0], img)),
+                "transform_diff": float((a.transformation.matrix() - b.transformation.matrix(True)).abs().max()),
+                "thickness": [float(a.thickness), float(b.thickness)]}
+folder = os.path.join(tmp, "slices")
+os.makedirs(folder)
+rim.save_slices(folder, a[:])
+back = oim.load_slices(folder)
+out["nifti"]["slice_folder"] = len(back) == 4 and all(bool(torch.equal(x.image, y.image * y.mask)) for x, y in zip(back, a[:]))
 print(json.dumps(out))
 '''
 
@@ -73,7 +94,7 @@ def test_unmodified_reference_runs_on_the_standin_modules(native_lib):
     r = subprocess.run([sys.executable, "-c", f"ROOT={ROOT!r}; REF={REF!r}\n" + SCRIPT], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
-    assert out["installed"] == ["nesvor.slice_acq_cuda", "nesvor.transform_convert_cuda", "tinycudann"]
+    assert set(out["installed"]) >= {"nesvor.slice_acq_cuda", "nesvor.transform_convert_cuda", "tinycudann"}
     assert out["sa_is_ours"] and out["tc_is_ours"] and out["ref_file"].startswith(REF) and out["train_uses_ref_models"]
     assert out["encoding_class"] == "HashGridEncoding" and out["network_class"] == "FusedMLP"
     assert out["state_keys"] == ["bounding_box", "density_net.params", "encoding.params"] and all(out["same_shapes"].values())
@@ -81,17 +102,21 @@ def test_unmodified_reference_runs_on_the_standin_modules(native_lib):
     assert {"inr", "sigma_net", "b_net", "slice_embedding"} <= set(out["nesvor_modules"]) and out["b_net_params"] == 64 * 32 + 16 * 64
     for k, v in out["errors"].items():
         assert "must be a CUDA tensor" in v, (k, v)
+    nf = out["nifti"]  # files written by the reference's image.py (through the nibabel stand-in when nibabel is absent)
+    assert nf["slices_equal"] and nf["image_survives"] and nf["transform_diff"] < 1e-5 and nf["thickness"] == [3.0, 3.0] and nf["slice_folder"]
 
 
 def test_install_is_idempotent_and_reversible():
     import nesvor_b200.compat as compat
 
-    before = {n: sys.modules.get(n) for n in ("nesvor.slice_acq_cuda", "nesvor.transform_convert_cuda", "tinycudann")}
+    before = {n: sys.modules.get(n) for n in ("nesvor.slice_acq_cuda", "nesvor.transform_convert_cuda", "tinycudann", "nibabel", "nibabel.nifti1")}
     try:
         a = compat.install()
         b = compat.install()
         assert set(a) == set(b) and hasattr(sys.modules["tinycudann"], "Encoding")
-        assert compat.install(tcnn="never").keys() == {"nesvor.slice_acq_cuda", "nesvor.transform_convert_cuda"}
+        assert compat.install(tcnn="never", nibabel="never").keys() == {"nesvor.slice_acq_cuda", "nesvor.transform_convert_cuda"}
+        nib = compat.install(nibabel="force")["nibabel"]
+        assert callable(nib.load) and callable(nib.save) and nib.nifti1.Nifti1Image is nib.Nifti1Image
         for fn in ("forward", "backward", "adjoint_forward", "adjoint_backward"):
             assert callable(getattr(sys.modules["nesvor.slice_acq_cuda"], fn))
         compat.uninstall()

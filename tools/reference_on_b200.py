@@ -38,10 +38,6 @@ def main():
         print(json.dumps({"available": False, "why": "baseline/_ref/nesvor absent" if torch.cuda.is_available() else "no CUDA device"}))
         return
     sys.path.insert(0, REF_PARENT)
-    try:
-        import nibabel  # noqa: F401
-    except ImportError:
-        sys.modules["nibabel"] = types.ModuleType("nibabel")  # imported at module level by nesvor/image only
     import nesvor_b200.compat as compat
 
     compat.install()

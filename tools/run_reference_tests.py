@@ -41,10 +41,6 @@ def main():
     compat.install()
     sys.path.insert(0, REF_PARENT)  # `import nesvor`, `import tests` now resolve to the reference's copies
     os.chdir(REF_PARENT)
-    try:
-        import nibabel  # noqa: F401
-    except ImportError:
-        sys.modules["nibabel"] = types.ModuleType("nibabel")
     suite = unittest.defaultTestLoader.loadTestsFromNames(MODULES)
     stream = io.StringIO()
     res = unittest.TextTestRunner(stream=stream, verbosity=2).run(suite)
