@@ -5,7 +5,8 @@ artefacts are absent or unusable on the box.
 
   * kernel B and the pose converters  vs  the reference's own CUDA kernels on the same GPU (tools/kernel_b_vs_reference.py);
   * the reference's own NeSVoR / autograd wrappers on this library  vs  this package's mirror (tools/reference_on_b200.py);
-  * the reference's own unittest modules for the path, unmodified, on this library (tools/run_reference_tests.py).
+  * the reference's own unittest modules for the path, unmodified, on this library (tools/run_reference_tests.py);
+  * the reference's own command line, `nesvor reconstruct`, end to end on this library (tools/reference_cli_on_b200.py).
 """
 import os
 import sys
@@ -98,3 +99,26 @@ def test_reference_own_unit_tests_pass_on_this_library(native_lib):
     print(line)
     assert "nesvor_b200" in (out["native_module"] or "")
     assert out["tests_run"] >= 6 and out["failures"] == 0 and out["errors"] == 0, out["details"]
+
+
+def test_reference_command_line_reconstruct_runs_on_this_library(native_lib):
+    """`nesvor reconstruct --input-slices ... --output-volume ... --output-model ...` through the reference's own
+    `nesvor.cli.main.main()` (argument parser, inputs(), train(), sample_volume(), sample_slices(), outputs()), unmodified,
+    on this library via nesvor_b200.compat (tools/reference_cli_on_b200.py, subprocess): motion-corrupted phantom stacks
+    written as a NIfTI slice folder in, reconstructed volume + model out; the volume is scored against the phantom.
+    Skipped when the reference copy is absent or the command cannot run on this box."""
+    import json
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "reference_cli_on_b200.py")], capture_output=True, text=True, timeout=1200)
+    line = next((l for l in reversed(r.stdout.splitlines()) if l.startswith("{")), None)
+    if r.returncode != 0 or line is None:
+        pytest.skip("reference command line did not run here: " + (r.stderr or r.stdout)[-500:])
+    out = json.loads(line)
+    if not out.get("available"):
+        pytest.skip("reference copy not available: " + str(out.get("why")))
+    print(line)
+    assert "baseline/_ref" in out["reference_train_file"].replace(os.sep, "/")
+    assert out["finite"] and out["model_written"] and out["masked_voxels"] > 1000
+    assert out["psnr_inside"] > 10.0, out

@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""`nesvor reconstruct` -- the reference's OWN command line, unmodified -- on libnesvor_b200 (GPU box).
+
+baseline/_ref/nesvor is the reference's Python layer exactly as under /root/reference; nesvor_b200.compat supplies its
+native imports (slice_acq_cuda, transform_convert_cuda, tinycudann) and, when nibabel is absent, the three nibabel calls it
+makes.  This script
+
+  1. simulates motion-corrupted stacks of the 3-D Shepp-Logan phantom with this package's simulator (kernel B) and writes
+     them as a NIfTI slice folder (each slice with its true pose, as after registration);
+  2. calls `nesvor.cli.main.main()` with
+         nesvor reconstruct --input-slices <folder> --output-volume <out.nii.gz> --output-model <model.pt> --n-iter ... 
+     i.e. the reference's argument parser, `inputs()`, `train()`, `sample_volume()`, `sample_slices()`, `outputs()`;
+  3. reads the written volume back and scores it against the phantom at the volume's own voxel positions.
+
+Prints ONE JSON line ({"available": false, ...} without the reference copy or a GPU).
+"""
+import json
+import os
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+REF_PARENT = os.path.join(ROOT, "baseline", "_ref")
+
+
+def main():
+    import torch
+
+    if not os.path.isdir(os.path.join(REF_PARENT, "nesvor")) or not torch.cuda.is_available():
+        print(json.dumps({"available": False, "why": "baseline/_ref/nesvor absent" if torch.cuda.is_available() else "no CUDA device"}))
+        return
+    import nesvor_b200 as nb
+    import nesvor_b200.compat as compat
+    import psnr_phantom as pp
+    from nesvor_b200.data.phantom import simulate_slices, stack_geometry
+
+    dev = torch.device("cuda", 0)
+    n, n_stacks, gap = 48, 3, 2.0
+    torch.manual_seed(0)
+    slices, volume, true_ax = simulate_slices(device=dev, n=n, n_stacks=n_stacks, res_r=1.0, res_s=1.0, gap=gap, motion_deg=3.0, motion_mm=1.5)
+    _, n_slice = stack_geometry(n, 1.0, 1.0, gap)
+    for s in slices:  # hand over the poses the data were acquired at (what registration would have produced)
+        i = s.stack_idx * n_slice + s.slice_idx
+        s.transformation = nb.RigidTransform(true_ax[i : i + 1].clone(), True)
+    tmp = tempfile.mkdtemp(prefix="nsv_cli_")
+    folder, out_vol, out_model = os.path.join(tmp, "slices"), os.path.join(tmp, "volume.nii.gz"), os.path.join(tmp, "model.pt")
+    nb.save_slices(folder, slices)
+
+    compat.install()
+    sys.path.insert(0, REF_PARENT)
+    import nesvor.cli.main as cli  # the reference's command line
+    import nesvor.nesvor.train as rtrain
+
+    n_iter = 1500
+    argv = ["nesvor", "reconstruct", "--input-slices", folder, "--output-volume", out_vol, "--output-model", out_model, "--n-iter", str(n_iter),
+            "--batch-size", "2048", "--n-samples", "64", "--output-resolution", "1.0", "--verbose", "0", "--seed", "0"]
+    old_argv = sys.argv
+    sys.argv = argv
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    try:
+        cli.main()
+    finally:
+        sys.argv = old_argv
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    # ---- score the written volume against the phantom at its own voxel positions
+    rec = nb.load_volume(out_vol, device=dev)
+    phantom = nb.Volume(volume[0, 0], volume[0, 0] > -1, nb.RigidTransform(torch.zeros(1, 6, device=dev), True), 1.0, 1.0, 1.0)
+    m = rec.mask
+    xyz = rec.xyz_masked
+    gt = phantom.sample_points(xyz)
+    inside = gt > 0
+    out = {"available": True, "argv": argv[1:], "reference_train_file": rtrain.__file__, "n_slices": len(slices), "wall_s": wall,
+           "queries": n_iter * 2048 * 64, "queries_per_s_wall_whole_command": n_iter * 2048 * 64 / wall,
+           "volume_shape": list(rec.image.shape), "masked_voxels": int(m.sum()), "finite": bool(torch.isfinite(rec.image).all()),
+           "psnr_inside": pp.psnr(rec.image[m][inside].cpu(), gt[inside].cpu()), "model_written": os.path.exists(out_model)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
