@@ -197,3 +197,28 @@ def test_save_load_stack_volume_and_slices(tmp_path):
     # 4-D input with a singleton channel and a 4-D file are handled like the reference does
     save_nii_volume(str(tmp_path / "c.nii"), img[:, None], None)
     assert load_volume(str(tmp_path / "c.nii")).image.shape == (d, h, w)
+
+
+def test_nifti_quaternion_convention_against_scipy():
+    """NIfTI's (a, b, c, d) is the unit quaternion (w, x, y, z) with a >= 0 recovered from b, c, d (nifti1.h: "quatern_b,
+    quatern_c, quatern_d"); checked against scipy's independent implementation, with spacings and qfac applied per column."""
+    from scipy.spatial.transform import Rotation
+
+    from nesvor_b200.image.nifti import mat44_to_quatern, quatern_to_mat44
+
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        if q[0] < 0:
+            q = -q
+        a, b, c, d = q
+        dx, dy, dz = rng.uniform(0.5, 3.0, 3)
+        for qfac in (1.0, -1.0):
+            M = quatern_to_mat44(b, c, d, 1.0, 2.0, 3.0, dx, dy, dz, qfac)
+            R = Rotation.from_quat([b, c, d, a]).as_matrix()  # scipy: scalar-last
+            np.testing.assert_allclose(M[:3, :3], R @ np.diag([dx, dy, dz * qfac]), atol=1e-12)
+            np.testing.assert_allclose(M[:3, 3], [1.0, 2.0, 3.0])
+            b2, c2, d2, *_rest, qf2 = mat44_to_quatern(M)
+            assert qf2 == qfac
+            np.testing.assert_allclose([b2, c2, d2], [b, c, d], atol=1e-9)
