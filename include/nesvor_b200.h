@@ -85,6 +85,17 @@ int nsv_slice_acq_adjoint_backward_f32(const float* transforms, float* grad_vol,
                                        const uint8_t* slices_mask, const float* vol, float* grad_slices,
                                        float* grad_transforms, int D, int H, int W, int d_p, int h_p, int w_p, int n,
                                        int h, int w, float res_slice, int interp_psf, int equalize, void* stream);
+/* Flavour switch of the fp32 slice-acquisition family.  0 (default; or env NSV_SLICE_ACQ_EXACT unset): the fast product
+ * kernels (csrc/slice_acq_fast.cu: FMA contraction, inside / outside pixel classification, per-slice rotated tap table,
+ * axis-matched volume layouts, neighbour-merged reductions) -- equal to the reference within fp32 round-off.
+ * 1: the bit-exact flavour (csrc/slice_acq.cu, -fmad=false) whose gather passes reproduce the reference's C arithmetic
+ * (slice_acq_cuda_kernel.cu:18-171, :696-950 as compiled for the CPU) bit for bit -- verification mode.
+ * nsv_set_slice_acq_tuning: bit mask of the fast flavour's optimisations (1 layouts, 2 row warps, 4 neighbour merge,
+ * 8 zero-pixel skip in A^T, 16 pixel classification); profiling / test hook, default all on. */
+void nsv_set_slice_acq_exact(int exact);
+int nsv_get_slice_acq_exact(void);
+void nsv_set_slice_acq_tuning(unsigned bits);
+unsigned nsv_get_slice_acq_tuning(void);
 int nsv_equalize_f32(float* vol, const float* vol_weight, int is_grad, int64_t DHW, void* stream);
 
 int nsv_slice_acq_forward_f64(const double* transforms, const double* vol, const uint8_t* vol_mask,

@@ -17,8 +17,13 @@ encoding_config, dtype)` and `Network(n_input_dims, n_output_dims, network_confi
     import nesvor_b200.compat as compat; compat.install()
     import nesvor                                   # the reference, untouched
 
-the reference's own `INR`, `NeSVoR`, `train`, `slice_acquisition`, `RigidTransform`, SRR ... run on the B200 kernels
-(the unfused path: one native op per reference op; the fused iteration is `nesvor_b200.train(..., args.fused=True)`).
+the reference's own `INR`, `NeSVoR`, `slice_acquisition`, `RigidTransform`, SRR ... run on the B200 kernels, one native op
+per reference op.  For the hot loop that is not enough (one launch per op: 5-6 ms per iteration against 0.8 ms), so
+`install(fused=True)` (the default) ALSO rebinds `nesvor.nesvor.train.train` -- what `nesvor reconstruct` calls
+(nesvor/cli/commands.py:111) -- to `fused_train` below: the reference's own `Dataset` and `NeSVoR` classes, the reference's
+loop structure (train.py:123-232), but each iteration is ONE launch of kernel A + the fused AdamW (`FusedTrainer.step`); the
+INR it returns renders through `nsv_inr_render` underneath the reference's unmodified `sample_volume / sample_slices`.
+Configurations kernel A is not instantiated for fall back to the reference's own `train` on the per-op path, with a warning.
 A real `tinycudann` / `nibabel`, if installed, is left alone unless `tcnn="force"` / `nibabel="force"`; the nibabel stand-in
 covers single-file NIfTI-1 (`image/nifti.py`).
 """
@@ -138,9 +143,133 @@ def _have_real(name: str) -> bool:
         return False
 
 
-def install(tcnn: str = "auto", nibabel: str = "auto") -> dict:
+_REF_TRAIN = None  # the reference's own train(), kept for configurations outside kernel A's instantiations
+LAST_TRAIN_INFO: dict = {}  # what the last fused_train call did (path taken, ms per iteration): read by tools / tests
+
+
+class _DeferredBatch:
+    """What the fused INR's `sample_batch` hands to its `forward`: the un-expanded request (sample.py:25-31,44-50)."""
+
+    def __init__(self, xyz, transformation, psf_sigma, n_samples):
+        self.xyz, self.transformation, self.psf_sigma, self.n_samples = xyz, transformation, psf_sigma, n_samples
+
+
+def _attach_fused_render(inr, args) -> None:
+    """Makes `inr.sample_batch(...)` + `inr(batch, False).mean(-1)` -- the two calls of the reference's sample.py:25-31 and
+    :44-50 -- one launch of the forward-only fused kernel `nsv_inr_render`: sample_batch defers, forward renders and returns
+    [M, 1] so that the caller's `.mean(-1)` is the identity.  Plain tensors still take the module's own forward."""
+    from .nesvor.fused import attach_render_state, fused_render
+
+    attach_render_state(inr, args)
+    plain_forward = inr.forward
+
+    def sample_batch(xyz, transformation, psf_sigma, n_samples):
+        return _DeferredBatch(xyz, transformation, psf_sigma, n_samples)
+
+    def forward(x, return_all=True):
+        if isinstance(x, _DeferredBatch):
+            return fused_render(inr, x.xyz, x.transformation, x.psf_sigma, x.n_samples)[:, None]
+        return plain_forward(x, return_all)
+
+    inr.sample_batch, inr.forward = sample_batch, forward
+
+
+def fused_train(slices, args):
+    """Drop-in for the reference's `train(slices, args) -> (INR, List[Slice], Volume)` (nesvor/nesvor/train.py:123-232).
+
+    Same data path and bookkeeping, built from the REFERENCE'S OWN classes (its `Dataset`: pixel table, epoch shuffle,
+    bounding box, mean, output mask; its `NeSVoR` on the tinycudann stand-ins; its `TrainLogger`), same optimiser
+    hyper-parameters, milestones and LR decay -- but the body of the loop (train.py:183-197: autocast forward, scaled
+    backward, AdamW step, zero_grad) is `FusedTrainer.step`: kernel A + finalize (+ transReg) + the fused AdamW.  The
+    reference reads every loss back every iteration (`.item()`, train.py:199-200: 5-6 host syncs); here the bias-corrected
+    moving average (utils/misc.py:91-122, alpha = 0.999) is kept on the device and read only when a log line is printed."""
+    import datetime
+    import logging
+    import time
+
+    import nesvor.nesvor.train as rt
+
+    from .nesvor.fused import FusedTrainer, FusedUnsupported
+
+    dataset = rt.Dataset(slices, args)
+    model = rt.NeSVoR(dataset.transformation, dataset.resolution, dataset.mean, dataset.bounding_box, args)
+    LAST_TRAIN_INFO.clear()
+    try:
+        if args.single_precision:
+            raise FusedUnsupported("--single-precision selects the fp32 nn.Linear MLPs (with biases)")
+        trainer = FusedTrainer(model, args)
+        batch = dataset.get_batch(args.batch_size, args.device)
+        first = trainer.step(**batch)  # the launch itself reports a configuration without an instantiation
+    except FusedUnsupported as e:
+        logging.warning("nesvor_b200: %s -- training on the per-op native path (reference loop)", e)
+        LAST_TRAIN_INFO.update(path="reference loop on per-op native kernels", why=str(e))
+        return _REF_TRAIN(slices, args)
+    logging.debug(rt.log_params(model))
+    decay_milestones = [int(m * args.n_iter) for m in args.milestones]
+    model.train()
+    keys = list(first.keys())
+    alpha = 1 - 0.001
+    ema = torch.zeros(len(keys), dtype=torch.float32, device=args.device)
+    train_logger = None
+    logging.info("NeSVoR training starts (nesvor_b200 fused iteration).")
+    torch.cuda.synchronize(args.device)
+    t_start = time.time()
+    losses = first
+    for i in range(1, args.n_iter + 1):
+        if i > 1:
+            batch = dataset.get_batch(args.batch_size, args.device)
+            losses = trainer.step(**batch)
+        ema.mul_(alpha).add_(torch.stack([losses[k] for k in keys]), alpha=1 - alpha)
+        if (decay_milestones and i >= decay_milestones[0]) or i == args.n_iter:
+            if train_logger is None:
+                train_logger = rt.TrainLogger("time", "epoch", "iter", *keys, "lr")
+            avg = (ema / (1 - alpha**i)).tolist()  # the only device read-back of the loop
+            train_logger.log(datetime.timedelta(seconds=int(time.time() - t_start)), dataset.epoch, i, *avg, trainer.lr)
+            if i < args.n_iter:
+                decay_milestones.pop(0)
+                trainer.decay_lr(args.gamma)
+    torch.cuda.synchronize(args.device)
+    wall = time.time() - t_start
+    LAST_TRAIN_INFO.update(path="fused (kernel A + fused AdamW)", iterations=args.n_iter, ms_per_iteration=1e3 * wall / max(args.n_iter, 1),
+                           queries_per_iteration=args.batch_size * args.n_samples, launches_per_iteration=4 if trainer.pose else 3,
+                           n_levels=int(model.inr.encoding.n_levels), n_pixels=int(dataset.xyz.shape[0]))
+    trainer.sync_to_model()
+    _attach_fused_render(model.inr, args)
+    # outputs (train.py:223-232)
+    transformation = model.transformation
+    dataset.transformation = transformation
+    mask = dataset.mask
+    output_slices = []
+    for i in range(len(slices)):
+        output_slice = slices[i].clone()
+        output_slice.transformation = transformation[i]
+        output_slices.append(output_slice)
+    return model.inr, output_slices, mask
+
+
+def _install_fused_train() -> None:
+    """Rebinds `train` where the reference looks it up: the defining module and, if already imported, the command module
+    that did `from ..nesvor.train import train` (nesvor/cli/commands.py)."""
+    global _REF_TRAIN
+    rt = importlib.import_module("nesvor.nesvor.train")
+    if getattr(rt.train, "__nesvor_b200_fused__", False):
+        return
+    _REF_TRAIN = rt.train
+    fused_train.__nesvor_b200_fused__ = True
+    rt.train = fused_train
+    pkg = sys.modules.get("nesvor.nesvor")
+    if pkg is not None and getattr(pkg, "train", None) is _REF_TRAIN:
+        pkg.train = fused_train
+    cmd = sys.modules.get("nesvor.cli.commands")
+    if cmd is not None and getattr(cmd, "train", None) is _REF_TRAIN:
+        cmd.train = fused_train
+
+
+def install(tcnn: str = "auto", nibabel: str = "auto", fused: bool = True) -> dict:
     """Registers the stand-in modules in `sys.modules`; returns {name: module} of what was installed.
-    tcnn / nibabel = "auto": only when no real `tinycudann` / `nibabel` is importable; "force": always; "never": leave it alone."""
+    tcnn / nibabel = "auto": only when no real `tinycudann` / `nibabel` is importable; "force": always; "never": leave it alone.
+    fused: also rebind the reference's `train` to `fused_train` (needs the reference package `nesvor` on sys.path; silently
+    skipped when it is not importable yet -- call `install()` again after adding it)."""
     done = {}
     for name, make in (("nesvor.slice_acq_cuda", _slice_acq_module), ("nesvor.transform_convert_cuda", _transform_convert_module)):
         sys.modules[name] = done[name] = make()
@@ -154,6 +283,12 @@ def install(tcnn: str = "auto", nibabel: str = "auto") -> dict:
     if parent is not None:
         for name in ("slice_acq_cuda", "transform_convert_cuda"):
             setattr(parent, name, sys.modules["nesvor." + name])
+    if fused:
+        try:
+            _install_fused_train()
+            done["nesvor.nesvor.train.train"] = fused_train
+        except ImportError:
+            pass
     return done
 
 

@@ -23,7 +23,8 @@ COMMON_FLAGS = [
 SOURCES = {
     "common.cu": [],
     "transform_convert.cu": ["-fmad=false"],  # literal C arithmetic of the reference converters
-    "slice_acq.cu": ["-fmad=false"],  # gather passes reproduce the CPU oracle bit for bit
+    "slice_acq.cu": ["-fmad=false"],  # bit-exact flavour: gather passes reproduce the CPU oracle bit for bit
+    "slice_acq_fast.cu": [],  # product flavour (FMA) + the C ABI of the family
     "hashgrid.cu": [],
     "mlp.cu": [],
     "inr_fused.cu": [],

@@ -64,24 +64,32 @@ def _adapt_mlp(flat: torch.Tensor, net) -> torch.Tensor:
 
 
 def load_model(path: str, device, args: Optional[Namespace] = None) -> Tuple[INR, Volume, Namespace]:
-    """-> (INR with the checkpoint's parameters, mask Volume, the checkpoint's args overridden by `args`)."""
+    """-> (INR with the checkpoint's parameters, mask Volume, the checkpoint's args overridden by `args`).
+
+    Like the reference (cli/io.py:24-29,53-59) the network is built STRICTLY from the checkpoint's own args -- the caller's
+    namespace (which `inputs()` passes in full, model hyper-parameters included) must never change the architecture the
+    stored parameters are decoded with -- and the two namespaces are merged only afterwards, for downstream use."""
     cp = torch.load(path, map_location=device, weights_only=False, pickle_module=_pickle_module)
     cp_args = cp["args"]
-    merged = Namespace(**vars(cp_args))
-    if args is not None:
-        for k, v in vars(args).items():
-            setattr(merged, k, v)
-    merged.device = device
-    if not hasattr(merged, "dtype"):
-        merged.dtype = torch.float32 if getattr(merged, "single_precision", False) else torch.float16
+    build = Namespace(**vars(cp_args))
+    build.device = device
+    if not hasattr(build, "dtype"):
+        build.dtype = torch.float32 if getattr(build, "single_precision", False) else torch.float16
     state = dict(cp["model"])
-    inr = INR(state["bounding_box"].to(device), merged)
+    inr = INR(state["bounding_box"].to(device), build)
     for name, net in (("density_net", inr.density_net),):
         key = f"{name}.params"
         if key in state and hasattr(net, "layer_shapes"):
             state[key] = _adapt_mlp(state[key].float(), net)
     state["encoding.params"] = state["encoding.params"].float()
     inr.load_state_dict(state)
+    merged = Namespace(**vars(cp_args))  # utils/misc.py:22-26 merge_args: the caller's values win
+    if args is not None:
+        for k, v in vars(args).items():
+            setattr(merged, k, v)
+    merged.device = device
+    if not hasattr(merged, "dtype"):
+        merged.dtype = build.dtype
     return inr.to(device), cp["mask"], merged
 
 

@@ -176,6 +176,13 @@ class FusedState:
         self.peer_tail32 = (ctypes.c_void_p * world)(*[p + n_grad_pad + n_f16_pad for p in ptrs]) if n_tail > 0 else None
         handle.barrier()  # every rank's copy is initialised before anyone's optimiser writes into it
 
+    def disable_peer_memory(self) -> None:
+        """Back to private buffers (another rank could not set peer memory up: the ranks fall back together)."""
+        self.grad, self.flat16 = self.grad.clone(), self.flat16.clone()
+        self.losses = self.grad[self.n_total : self.n_total + 8]
+        self.tail32 = None
+        self._symm_buf = self.peer_handle = self.peer_grads = self.peer_flat16 = self.peer_tail32 = None
+
     # ------------------------------------------------------------------ model <-> flat
     def seg(self, name: str, buf: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         if name not in self.offsets:
@@ -328,15 +335,24 @@ class FusedTrainer:
         want = getattr(self.args, "dp_optimizer", "auto")
         mode = "allreduce"
         if want in ("auto", "peer") and world > 1 and self.state.device.type == "cuda" and dist.get_backend() == "nccl" and world <= 16:
+            err = None
             try:
                 self.state.enable_peer_memory(dist.group.WORLD)
                 mode = "peer"
             except Exception as e:  # symmetric memory unavailable (no peer access, old driver, ...)
+                err = e
+            # the ranks must AGREE: one rank in handle.barrier() while another sits in dist.all_reduce() is a deadlock
+            ok = torch.tensor([1 if mode == "peer" else 0], dtype=torch.int32, device=self.state.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
                 if want == "peer":
-                    raise
+                    raise RuntimeError(f"dp_optimizer='peer': peer memory could not be set up on every rank ({err})")
+                if mode == "peer":
+                    self.state.disable_peer_memory()
+                mode = "allreduce"
                 import logging
 
-                logging.warning("peer-memory optimiser unavailable (%s); using NCCL all-reduce + AdamW", e)
+                logging.warning("peer-memory optimiser unavailable on some rank (%s); using NCCL all-reduce + AdamW", err)
         elif want == "peer":
             raise RuntimeError("dp_optimizer='peer' needs NCCL ranks on CUDA devices (world <= 16)")
         self.dp_mode = mode
@@ -468,10 +484,14 @@ def fused_render(inr: INR, xyz: torch.Tensor, transformation: Optional[RigidTran
     prm = state.params_struct()
     if noise is not None:
         noise = noise.contiguous().float()
+    # every launch continues the Philox stream where the previous one stopped: the reference draws fresh randn per batch
+    # (models.py:161-169), so the Monte-Carlo error of successive inference chunks / slices must be independent
+    offset = getattr(state, "render_offset", 0)
+    state.render_offset = offset + M * S
     with torch.cuda.device(xyz.device):
         rc = _lib.lib().nsv_inr_render(
             ctypes.byref(state.cfg), ctypes.byref(prm), _lib.ptr(xyz), _lib.ptr(mat), ctypes.c_int(per_point), _lib.ptr(sig),
-            ctypes.c_int(sig_pp), _lib.ptr(noise), ctypes.c_uint64(seed), ctypes.c_uint64(0), _lib.ptr(out), ctypes.c_int64(M),
+            ctypes.c_int(sig_pp), _lib.ptr(noise), ctypes.c_uint64(seed), ctypes.c_uint64(offset), _lib.ptr(out), ctypes.c_int64(M),
             ctypes.c_int(S), _lib.stream(xyz.device))
     if rc == -2:
         raise FusedUnsupported(_lib.lib().nsv_last_error_string().decode())

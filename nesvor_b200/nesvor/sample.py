@@ -19,8 +19,12 @@ def _render(model: INR, xyz, transformation, psf_sigma, n_samples: int, args: Na
     if getattr(args, "fused", False):
         from .fused import attach_render_state, fused_render
 
-        if getattr(model, "_fused_state", None) is None:
-            attach_render_state(model, args)  # snapshot of the (trained) parameters in kernel layout
+        st = getattr(model, "_fused_state", None)
+        if st is None:
+            st = attach_render_state(model, args)  # snapshot of the parameters in kernel layout
+        elif getattr(st, "param_version", None) != model.encoding.params._version:
+            st.pull_from_model()  # the INR was trained / loaded since the snapshot was taken
+        st.param_version = model.encoding.params._version
         return fused_render(model, xyz, transformation, psf_sigma, n_samples)
     xyz_batch = model.sample_batch(xyz, transformation, psf_sigma, n_samples)
     return model(xyz_batch, False).mean(-1)

@@ -17,33 +17,37 @@ pytestmark = pytest.mark.gpu
 
 
 def test_against_reference_cuda_extension_on_the_gpu(native_lib):
-    """Kernel B vs the reference's OWN CUDA extension compiled for sm_100a (oracle/build_ref_gpu.sh: slice_acq_cuda.cpp +
-    slice_acq_cuda_kernel.cu from /root/reference with the one-token torch-2.x fix), same inputs, same GPU, all four
-    operators, with and without masks (tools/kernel_b_vs_reference.py, run in a subprocess so that a foreign kernel can
-    never poison this process's CUDA context).  The reference kernels are compiled with FMA contraction and scatter with
-    atomics, ours reproduce the un-contracted CPU arithmetic (-fmad=false): agreement is at fp32 round-off -- relative L2
-    <= 1e-5 for the gathers, 1e-4 for the scatter passes, 1e-3 for the pose gradients.  Skipped when the prebuilt
-    extension is absent or cannot be loaded / called on this box."""
+    """Kernel B (the product's fast FMA build AND the bit-exact -fmad=false build) vs the reference's OWN CUDA extension
+    compiled for sm_100a (oracle/build_ref_gpu.sh: slice_acq_cuda.cpp + slice_acq_cuda_kernel.cu from /root/reference with the
+    one-token torch-2.x fix), same inputs, same GPU, all four operators, with and without masks
+    (tools/kernel_b_vs_reference.py, run in a subprocess so that a foreign kernel can never poison this process's CUDA
+    context).  Two fp32 implementations that sum thousands of terms in different orders (atomics, FMA contraction) differ
+    at round-off, and for an ill-conditioned output (the 12 pose-gradient sums) nobody can say a priori by how much: the
+    yardstick is the fp64 evaluation of the same operator (this library's _f64 entry points).  Bar: ours is at least as
+    close to fp64 as the reference's own kernel is (x2 for run-to-run atomic-order noise), or below an absolute round-off
+    floor.  Skipped when the prebuilt extension is absent or cannot be loaded / called on this box."""
     import json
     import subprocess
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "kernel_b_vs_reference.py"), "--reps", "0"], capture_output=True, text=True, timeout=600)
-    line = next((l for l in reversed(r.stdout.splitlines()) if l.startswith("{")), None)
-    if r.returncode != 0 or line is None:
-        pytest.skip("reference CUDA extension check did not run here: " + (r.stderr or r.stdout)[-300:])
-    out = json.loads(line)
-    if not out.get("available"):
-        pytest.skip("reference CUDA extension not available: " + str(out.get("why")))
-    print(line)
-    for case, errs in out["rel_l2"].items():
-        for k, err in errs.items():
-            if case == "pose_converters":  # same formulas, FMA-contracted vs literal arithmetic; the backward passes divide by sin / theta
-                assert err <= (1e-5 if k.endswith("fwd") else 1e-3), (case, k, err)
-                continue
-            tol = 1e-3 if k.endswith("grad_tf") else (1e-5 if k in ("slices", "weight") or k.endswith("adjbwd0_grad_slices") else 1e-4)
-            assert err <= tol, (case, k, err)
+    for exact in (0, 1):
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "kernel_b_vs_reference.py"), "--reps", "0", "--exact", str(exact)],
+                           capture_output=True, text=True, timeout=600)
+        line = next((l for l in reversed(r.stdout.splitlines()) if l.startswith("{")), None)
+        if r.returncode != 0 or line is None:
+            pytest.skip("reference CUDA extension check did not run here: " + (r.stderr or r.stdout)[-300:])
+        out = json.loads(line)
+        if not out.get("available"):
+            pytest.skip("reference CUDA extension not available: " + str(out.get("why")))
+        print(line)
+        for case, errs in out["err_vs_f64"].items():
+            for k, e in errs.items():
+                floor = 5e-5 if k.endswith("grad_tf") else (2e-6 if k in ("slices", "weight") or k.endswith("grad_slices") else 5e-6)
+                assert e["ours"] <= max(2.0 * e["reference"], floor), (exact, case, k, e)
+        for k, err in out["rel_l2"]["pose_converters"].items():
+            # same formulas, FMA-contracted vs literal arithmetic; the backward passes divide by sin / theta
+            assert err <= (1e-5 if k.endswith("fwd") else 1e-3), (k, err)
 
 
 def test_unmodified_reference_package_runs_on_this_library(native_lib):
@@ -77,7 +81,9 @@ def test_unmodified_reference_package_runs_on_this_library(native_lib):
     w = out["wrappers"]
     assert w["slice_acquisition"] <= 1e-6 and w["adjoint_equalized"] <= 1e-5 and w["grad_finite"] and w["axisangle_round_trip"] <= 1e-4
     loop = out["reference_loop"]
-    assert loop["mse_last"] == loop["mse_last"] and loop["mse_last"] <= loop["mse_first"] * 1.05
+    # the optimised quantity is the weighted total (train.py:185-188); "MSE" alone is (v_out - v)^2 / (2 var) and may rise
+    # while the learnt variance shrinks (the targets of this check are uniform noise)
+    assert loop["total_last"] == loop["total_last"] and loop["total_last"] < loop["total_first"]
 
 
 def test_reference_own_unit_tests_pass_on_this_library(native_lib):
@@ -122,3 +128,10 @@ def test_reference_command_line_reconstruct_runs_on_this_library(native_lib):
     assert "baseline/_ref" in out["reference_train_file"].replace(os.sep, "/")
     assert out["finite"] and out["model_written"] and out["masked_voxels"] > 1000
     assert out["psnr_inside"] > 10.0, out
+    # the hot loop the command ran is the fused iteration (compat.fused_train), not one launch per reference op
+    assert out["train_is_fused_adapter"] and out["train"]["path"].startswith("fused"), out["train"]
+    c2 = out["config2_through_cli"]
+    assert "error" not in c2 and c2["path"].startswith("fused") and c2["n_levels"] == 16, c2
+    # BASELINE config 2 through the command line: within 10 % of bench.py's e2e figure for the same workload
+    # (0.885 ms per 2^20-query iteration through FusedTrainer.step with host batches, profiles/r02_bench_*.json)
+    assert c2["ms_per_iteration"] <= 1.0, c2

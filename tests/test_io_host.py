@@ -33,6 +33,30 @@ def test_save_load_round_trip(tmp_path):
     assert torch.equal(mask2.mask, mask.mask) and mask2.resolution_x == 0.8 and args2.width == 32
 
 
+def test_load_builds_the_network_from_the_checkpoints_own_args(tmp_path):
+    """cli/io.py:24-29: INR(cp["model"]["bounding_box"], cp["args"]) -- the caller's namespace, which `inputs()` passes in
+    full, must not change the architecture the stored parameters are decoded with (a different coarsest_resolution with
+    every level hashed would even keep the parameter count and silently decode on the wrong grid)."""
+    from nesvor_b200.image import Volume
+    from nesvor_b200.io import load_model, save_model
+    from nesvor_b200.nesvor.models import INR
+    from nesvor_b200.transform import RigidTransform
+
+    args = _args()
+    bb = torch.tensor([[-30.0, -30.0, -30.0], [30.0, 30.0, 30.0]])
+    inr = INR(bb, args)
+    mask = Volume(torch.ones(4, 5, 6), torch.ones(4, 5, 6, dtype=torch.bool), RigidTransform(torch.zeros(1, 6)), 0.8, 0.8, 0.8)
+    path = str(tmp_path / "model.pt")
+    save_model(path, inr, mask, args)
+    caller = _args(width=64, depth=2, coarsest_resolution=8.0, finest_resolution=1.0, log2_hashmap_size=10, n_features_z=7,
+                   inference_batch_size=123)
+    inr2, _, merged = load_model(path, torch.device("cpu"), caller)
+    for k, v in inr.state_dict().items():
+        assert torch.equal(v, inr2.state_dict()[k]), k
+    assert inr2.encoding.n_levels == inr.encoding.n_levels and inr2.encoding.meta.res[0] == inr.encoding.meta.res[0]
+    assert merged.width == 64 and merged.inference_batch_size == 123  # merged namespace: the caller's values win (utils/misc.py:22-26)
+
+
 def test_reads_reference_style_checkpoint(tmp_path):
     from nesvor_b200.io import load_model
     from nesvor_b200.nesvor.models import INR

@@ -28,9 +28,16 @@ def rel_l2(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
 
 
+def _lib_mode():
+    from nesvor_b200 import _lib
+
+    return int(_lib.lib().nsv_get_slice_acq_exact())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--exact", type=int, default=-1, help="1: the bit-exact (-fmad=false) kernels, 0: the fast product kernels, -1: library default")
     a = ap.parse_args()
     import torch
 
@@ -45,6 +52,11 @@ def main():
     from helpers import cuda, slice_acq_case
 
     sa = importlib.import_module("nesvor_b200.slice_acquisition.slice_acq")
+    if a.exact >= 0:
+        from nesvor_b200 import _lib
+
+        if hasattr(_lib.lib(), "nsv_set_slice_acq_exact"):
+            _lib.lib().nsv_set_slice_acq_exact(int(a.exact))
     empty = torch.empty(0, device="cuda")
     out = {"available": True, "rel_l2": {}}
     for masks in (False, True):
@@ -68,8 +80,21 @@ def main():
                 tf, gv.clone(), rvw, vm, psf, slices, sm, ro[0] if eq else empty, res, False, bool(eq), True, True)
             o[f"adjbwd{eq}_grad_slices"], o[f"adjbwd{eq}_grad_tf"] = sa.adjoint_backward(
                 tf, gv.clone(), ovw, ovm, psf, slices, osm, ov, res, False, eq, True, True)
+        # fp64 adjudication: the same operators through this library's _f64 entry points on the double-cast inputs are
+        # the common yardstick -- err(ours, f64) and err(reference, f64) say which fp32 implementation is closer to the truth
+        d = lambda t: t.double() if t is not None and t.numel() and t.is_floating_point() else t
+        t64 = {}
+        t64["slices"], t64["weight"] = sa.forward(d(tf), d(vol), ovm, osm, d(psf), c["slice_shape"], res, True, False)
+        t64["bwd_grad_vol"], t64["bwd_grad_tf"] = sa.backward(d(tf), d(vol), ovm, d(psf), d(gs), osm, res, False, True, True)
+        for eq in (0, 1):
+            tv, tvw = sa.adjoint_forward(d(tf), d(psf), d(slices), osm, ovm, c["vol_shape"], res, False, eq)
+            t64[f"adj{eq}_vol"] = tv
+            t64[f"adjbwd{eq}_grad_slices"], t64[f"adjbwd{eq}_grad_tf"] = sa.adjoint_backward(
+                d(tf), d(gv).clone(), tvw, ovm, d(psf), d(slices), osm, tv, res, False, eq, True, True)
         torch.cuda.synchronize()
-        out["rel_l2"]["masked" if masks else "plain"] = {k: rel_l2(o[k], r[k]) for k in r}
+        tag = "masked" if masks else "plain"
+        out["rel_l2"][tag] = {k: rel_l2(o[k], r[k]) for k in r}
+        out.setdefault("err_vs_f64", {})[tag] = {k: {"ours": rel_l2(o[k], t64[k]), "reference": rel_l2(r[k], t64[k])} for k in r}
     # ---- pose converters vs the reference's transform_convert_cuda (all four functions)
     tc = ref_gpu.load_transform()
     if tc is not None:
@@ -128,10 +153,29 @@ def main():
         s_our, t_our_f = timed(lambda: sa.forward(mat, vol, None, None, psf, (ss, ss), 1.0, False, False)[0])
         _, t_ref_a = timed(lambda: ref.adjoint_forward(mat, psf, s_ref, empty, empty, [n, n, n], 1.0, False, False)[0])
         _, t_our_a = timed(lambda: sa.adjoint_forward(mat, psf, s_our, None, None, (n, n, n), 1.0, False, False)[0])
+        # equalised adjoint (the SRR / PSFreconstruction call, svort/srr.py:118) writes vol and vol_weight
+        (v_ref, vw_ref), t_ref_ae = timed(lambda: ref.adjoint_forward(mat, psf, s_ref, empty, empty, [n, n, n], 1.0, False, True)[:2])
+        (v_our, vw_our), t_our_ae = timed(lambda: sa.adjoint_forward(mat, psf, s_our, None, None, (n, n, n), 1.0, False, True)[:2])
+        g = torch.Generator().manual_seed(11)
+        gs_full = torch.randn(s_ref.shape, generator=g).to(dev) * (s_ref > 0)  # cotangent on the acquired pixels
+        gv_full = torch.randn(vol.shape, generator=g).to(dev)
+        rb, t_ref_b = timed(lambda: ref.backward(mat, vol, empty, psf, gs_full, empty, 1.0, False, True, True))
+        ob, t_our_b = timed(lambda: sa.backward(mat, vol, None, psf, gs_full, None, 1.0, False, True, True))
+        rab, t_ref_ab = timed(lambda: ref.adjoint_backward(mat, gv_full, empty, empty, psf, s_ref, empty, empty, 1.0, False, False, True, True))
+        oab, t_our_ab = timed(lambda: sa.adjoint_backward(mat, gv_full, None, None, psf, s_our, None, None, 1.0, False, 0, True, True))
+        pair = lambda a_, b_: {"reference_cuda_extension": a_, "nesvor_b200": b_, "speedup": a_ / b_}
         out["config2_stack_simulation_ms"] = {"slices": int(s_ref.shape[0]), "slice_shape": [ss, ss], "psf_taps": int((psf != 0).sum()),
-                                              "forward": {"reference_cuda_extension": t_ref_f, "nesvor_b200": t_our_f},
-                                              "adjoint_forward": {"reference_cuda_extension": t_ref_a, "nesvor_b200": t_our_a},
-                                              "forward_rel_l2": rel_l2(s_our, s_ref)}
+                                              "forward": pair(t_ref_f, t_our_f), "backward": pair(t_ref_b, t_our_b),
+                                              "adjoint_forward": pair(t_ref_a, t_our_a), "adjoint_forward_equalize": pair(t_ref_ae, t_our_ae),
+                                              "adjoint_backward": pair(t_ref_ab, t_our_ab),
+                                              "rel_l2_ours_vs_reference": {"forward": rel_l2(s_our, s_ref), "adjoint_equalized_vol": rel_l2(v_our, v_ref),
+                                                                           "backward_grad_vol": rel_l2(ob[0], rb[0]), "backward_grad_tf": rel_l2(ob[1], rb[1]),
+                                                                           "adjoint_backward_grad_slices": rel_l2(oab[0], rab[0]),
+                                                                           "adjoint_backward_grad_tf": rel_l2(oab[1], rab[1])}}
+        try:
+            out["slice_acq_mode"] = "exact" if _lib_mode() else "fast"
+        except Exception:
+            pass
     print(json.dumps(out))
 
 

@@ -49,8 +49,8 @@ def main():
     folder, out_vol, out_model = os.path.join(tmp, "slices"), os.path.join(tmp, "volume.nii.gz"), os.path.join(tmp, "model.pt")
     nb.save_slices(folder, slices)
 
-    compat.install()
     sys.path.insert(0, REF_PARENT)
+    compat.install()  # native stand-ins + `train` rebound to the fused iteration (compat.fused_train)
     import nesvor.cli.main as cli  # the reference's command line
     import nesvor.nesvor.train as rtrain
 
@@ -67,6 +67,7 @@ def main():
         sys.argv = old_argv
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    train_info = dict(compat.LAST_TRAIN_INFO)
     # ---- score the written volume against the phantom at its own voxel positions
     rec = nb.load_volume(out_vol, device=dev)
     phantom = nb.Volume(volume[0, 0], volume[0, 0] > -1, nb.RigidTransform(torch.zeros(1, 6, device=dev), True), 1.0, 1.0, 1.0)
@@ -77,8 +78,40 @@ def main():
     out = {"available": True, "argv": argv[1:], "reference_train_file": rtrain.__file__, "n_slices": len(slices), "wall_s": wall,
            "queries": n_iter * 2048 * 64, "queries_per_s_wall_whole_command": n_iter * 2048 * 64 / wall,
            "volume_shape": list(rec.image.shape), "masked_voxels": int(m.sum()), "finite": bool(torch.isfinite(rec.image).all()),
-           "psnr_inside": pp.psnr(rec.image[m][inside].cpu(), gt[inside].cpu()), "model_written": os.path.exists(out_model)}
+           "psnr_inside": pp.psnr(rec.image[m][inside].cpu(), gt[inside].cpu()), "model_written": os.path.exists(out_model),
+           "train": train_info, "train_is_fused_adapter": bool(getattr(rtrain.train, "__nesvor_b200_fused__", False))}
+    # ---- the same command line on the BASELINE config-2 workload (bench.py's): ms per iteration of the hot loop as the CLI runs it
+    try:
+        out["config2_through_cli"] = config2_through_cli(cli, compat, nb, dev, tmp)
+    except Exception as e:  # the accuracy run above stands on its own
+        out["config2_through_cli"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     print(json.dumps(out))
+
+
+def config2_through_cli(cli, compat, nb, dev, tmp, n_iter=600):
+    """BASELINE config 2 (phantom 128^3, 3 orthogonal stacks, L = 16, T = 2^19, 64 x 3 hidden, 8192 px x 128 samples) through
+    `nesvor reconstruct`: what bench.py times through FusedTrainer.step, timed here inside the command the user runs."""
+    import torch
+
+    from nesvor_b200.data.phantom import simulate_slices
+
+    torch.manual_seed(0)
+    slices, _, _ = simulate_slices(device=dev, n=128, n_stacks=3, res_r=1.0, res_s=1.0, gap=3.0)
+    folder = os.path.join(tmp, "slices_cfg2")
+    nb.save_slices(folder, slices)
+    argv = ["nesvor", "reconstruct", "--input-slices", folder, "--output-model", os.path.join(tmp, "model_cfg2.pt"), "--n-iter", str(n_iter),
+            "--batch-size", "8192", "--n-samples", "128", "--depth", "3", "--finest-resolution", "0.119", "--no-pixel-variance",
+            "--no-slice-variance", "--no-transformation-optimization", "--verbose", "0", "--seed", "0"]
+    old_argv, sys.argv = sys.argv, argv
+    try:
+        cli.main()
+    finally:
+        sys.argv = old_argv
+    info = dict(compat.LAST_TRAIN_INFO)
+    info["argv"] = argv[1:]
+    if "ms_per_iteration" in info:
+        info["queries_per_s"] = info["queries_per_iteration"] / info["ms_per_iteration"] * 1e3
+    return info
 
 
 if __name__ == "__main__":

@@ -121,10 +121,10 @@ def main():
         scaler.step(opt)
         scaler.update()
         opt.zero_grad()
-        hist.append(float(losses["MSE"]))
+        hist.append((float(losses["MSE"]), float(loss)))
     e1.record()
     torch.cuda.synchronize()
-    out["reference_loop"] = {"iterations": n_it, "mse_first": hist[0], "mse_last": hist[-1], "ms_per_iteration": e0.elapsed_time(e1) / n_it,
+    out["reference_loop"] = {"iterations": n_it, "mse_first": hist[0][0], "mse_last": hist[-1][0], "total_first": hist[0][1], "total_last": hist[-1][1], "ms_per_iteration": e0.elapsed_time(e1) / n_it,
                              "queries_per_iteration": B * args.n_samples}
     print(json.dumps(out))
 
