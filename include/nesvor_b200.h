@@ -221,6 +221,10 @@ int nsv_set_fused_impl(int impl);
  * float-atomic ordering): `agg_max_entries` = largest dense level whose gradient is pre-reduced inside a warp before
  * touching global memory (0 = never, < 0 = default: every dense level, or $NSV_AGG_MAX); `fast_path` = 0 forces the generic
  * per-level loops, 1 the chunked branch-free loops, < 0 = default (1 or $NSV_FAST_PATH). */
+/* Number of leading dense levels of the fp16 table that the tcgen05 training kernel stages into shared memory with one
+ * bulk copy per CTA (TMA engine, cp.async.bulk) and gathers from there: -1 as many as fit beside the operand tiles
+ * (default; env NSV_SMEM_LEVELS), 0 none, -2 back to the default.  Profiling / test hook. */
+int nsv_set_fused_smem_levels(int levels);
 int nsv_set_fused_tuning(int64_t agg_max_entries, int fast_path);
 /* profiling hook: 16 int64 device counters that the tcgen05 kernel A (config-2 instantiation) fills with per-phase
  * warp cycles (gather, barriers, MMA wait, epilogues, losses, scatter, pixel barrier, -); NULL switches it off */

@@ -97,6 +97,9 @@ struct FusedArgs {
   long long* timers; // profiling only: 8 per-phase warp-cycle counters (device memory) or NULL
   uint32_t agg_max;  // tuning: warp-level gradient pre-reduction for dense levels with at most this many entries (0: off)
   int fast;          // tuning: 0 forces the generic (branchy) gather / scatter loops
+  int smem_levels;   // tcgen05 kernel: the first `smem_levels` (dense) levels of the fp16 table are bulk-copied (TMA engine,
+                     // cp.async.bulk) into shared memory once per CTA and gathered from there; -1: as many as fit, 0: none
+  uint32_t smem_table_bytes;  // set by the launcher: bytes of that table prefix
 };
 
 // ---- Philox4x32-10 + Box-Muller: three N(0,1) per (seed, sample index) ----
@@ -301,6 +304,9 @@ __device__ __forceinline__ void scatter_warp_generic(const float xn[3], const Le
 // raise `bad`; a warp with any bad lane redoes the tile with the generic loops, so results are identical.
 // =====================================================================================================
 __device__ __forceinline__ uint32_t ldg_u32(const __half2* p) { return __ldg(reinterpret_cast<const unsigned int*>(p)); }
+// dense levels: `lt.tbl[l]` is a GENERIC address -- global memory, or the CTA's shared-memory copy of a coarse level that
+// the tcgen05 kernel staged with cp.async.bulk (the load resolves the window at run time)
+__device__ __forceinline__ uint32_t ldx_u32(const __half2* p) { return *reinterpret_cast<const volatile unsigned int*>(p); }
 __device__ __forceinline__ float2 h2f2(uint32_t raw) { return __half22float2(*reinterpret_cast<const __half2*>(&raw)); }
 
 // floor + fraction with full-rate instructions only (FRND / F2I run at quarter rate): adding 1.5 * 2^23 with
@@ -364,6 +370,9 @@ __device__ __forceinline__ uint32_t encode_chunk(const float xn[3], const LevelT
     if (lt.ablate & 1u) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) raw[i][q] = e[q] & 0x03ff03ffu;
+    } else if (i < ND) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) raw[i][q] = ldx_u32(tl + e[q]);
     } else {
 #pragma unroll
       for (int q = 0; q < 4; ++q) raw[i][q] = ldg_u32(tl + e[q]);
@@ -483,7 +492,7 @@ __device__ __forceinline__ void scatter_chunk(const float xn[3], const LevelTabl
     if (kInputGrad) {
       const __half2* tl = lt.tbl[4 * c + i];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) raw[i][q] = ldg_u32(tl + e[i][q]);
+      for (int q = 0; q < 4; ++q) raw[i][q] = i < ND ? ldx_u32(tl + e[i][q]) : ldg_u32(tl + e[i][q]);
     }
   }
 #pragma unroll

@@ -677,11 +677,17 @@ namespace nsv { namespace fused {
 static int g_fused_impl = 0;
 static long g_agg_max = -1;  // -1: NSV_AGG_MAX or the built-in default
 static int g_fast_path = -1;
+static int g_smem_levels = -2;  // -2: NSV_SMEM_LEVELS or "as many as fit" (-1)
 static long long* g_timers = nullptr;
 } }
 
 extern "C" int nsv_set_fused_timers(void* device_counters) {
   nsv::fused::g_timers = (long long*)device_counters;
+  return NSV_OK;
+}
+
+extern "C" int nsv_set_fused_smem_levels(int levels) {
+  nsv::fused::g_smem_levels = levels < -1 ? -2 : levels;
   return NSV_OK;
 }
 
@@ -783,6 +789,9 @@ extern "C" int nsv_inr_train_step(const nsv_inr_config* cfg, const nsv_inr_param
     static const int fast_env = getenv("NSV_FAST_PATH") ? atoi(getenv("NSV_FAST_PATH")) : 1;
     a.agg_max = (uint32_t)(g_agg_max >= 0 ? g_agg_max : (agg_env < 0 ? 0 : agg_env));
     a.fast = g_fast_path >= 0 ? g_fast_path : fast_env;
+    static const int smem_env = getenv("NSV_SMEM_LEVELS") ? atoi(getenv("NSV_SMEM_LEVELS")) : -1;
+    a.smem_levels = g_smem_levels > -2 ? g_smem_levels : smem_env;
+    a.smem_table_bytes = 0;
     a.timers = g_timers;
     a.ablate = getenv("NSV_ABLATE") ? (uint32_t)atoi(getenv("NSV_ABLATE")) : 0u;  // profiling only, tcgen05 kernel
   }

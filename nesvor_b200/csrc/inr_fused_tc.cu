@@ -56,8 +56,9 @@ struct TcLayout {
   static constexpr size_t fz0 = 0, flv = 256, frho = 512, fxw = 768, fred = 768 + 768, flb = fred + 16 * 16;  // floats
   static constexpr size_t fend = flb + (BIAS ? 256 : 0);
   static constexpr size_t b_lt = b_scr + fend * 4;
-  static constexpr size_t b_sync = (b_lt + sizeof(LevelTable) + 15) / 16 * 16;  // mbar[2], tmem slot, flags
-  static constexpr size_t bytes = b_sync + 64;
+  static constexpr size_t b_sync = (b_lt + sizeof(LevelTable) + 15) / 16 * 16;  // mbar[2], tmem slot, flags, table mbarrier
+  static constexpr size_t bytes = (b_sync + 64 + 127) / 128 * 128;
+  // [bytes, bytes + staged table bytes): shared-memory copy of the coarsest levels of the fp16 hash table (FusedArgs::smem_levels)
   // ---- TMEM columns ----
   static constexpr uint32_t c_d = 0;                                      // group g: [64 g, 64 g + 64)
   static constexpr uint32_t c_w0 = 128;                                   // dW0   [64 x 32]
@@ -144,7 +145,11 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + L::b_sync) + grp;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::b_sync + 16);
   uint32_t* grp_ran = reinterpret_cast<uint32_t*>(smem + L::b_sync + 24);
+  uint64_t* tbar = reinterpret_cast<uint64_t*>(smem + L::b_sync + 32);  // completion of the staged-table bulk copy
   const nsv_inr_config& cfg = a.cfg;
+  // TMA-staged table prefix: levels [0, smem_levels) are contiguous at the start of the flat fp16 table (level-major tcnn
+  // layout, every level a multiple of 8 entries = 32 bytes), so ONE bulk copy per CTA brings them into shared memory
+  const uint32_t stab_bytes = a.smem_table_bytes;
 
   // ---- one-time setup: weights -> canonical tiles, level table, TMEM, mbarriers ----
   {
@@ -163,12 +168,20 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
       umma::stage_tile(wt + L::wbo, wb + 64 * 32, 16, 64, tid, kThreads);
     }
     stage_level_table(lt, cfg.grid, tid, a.agg_max, a.fast, a.table, a.g_table, a.ablate);
+    if (tid < a.smem_levels)  // same thread that wrote tbl[tid] above: the level is gathered from the shared-memory copy
+      lt.tbl[tid] = reinterpret_cast<const __half2*>(smem + L::bytes) + lt.offset[tid];
     if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
       umma::mbar_init(reinterpret_cast<uint64_t*>(smem + L::b_sync), 1);
       umma::mbar_init(reinterpret_cast<uint64_t*>(smem + L::b_sync) + 1, 1);
+      umma::mbar_init(tbar, 1);
       umma::mbar_fence_init();
       grp_ran[0] = grp_ran[1] = 0;
+      if (stab_bytes) {  // in flight while the CTA stages its weights; waited for before the first gather
+        umma::mbar_expect_tx(tbar, stab_bytes);
+        for (uint32_t o = 0; o < stab_bytes; o += 32768u)
+          umma::bulk_g2s(smem + L::bytes + o, reinterpret_cast<const unsigned char*>(a.table) + o, min(32768u, stab_bytes - o), tbar);
+      }
     }
   }
   float lse = 0.f;
@@ -186,6 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
+  if (stab_bytes) umma::mbar_wait(tbar, 0);
   const uint32_t tm = *tmem_slot;
   const uint32_t td = tm + L::c_d + 64u * grp;                       // this group's forward / dgrad region
   const uint32_t td2 = tm + L::c_d2 + 64u * grp;                     // BIAS: second region, so that b_net's products ride in the same MMA rounds
@@ -716,10 +730,22 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
 }
 
 template <int DEPTH, bool SIGMA, bool BIAS = false>
-int launch_tc(const FusedArgs& a, cudaStream_t st) {
+int launch_tc(const FusedArgs& a_in, cudaStream_t st) {
   using L = TcLayout<DEPTH, SIGMA, BIAS>;
   static_assert(L::bytes <= 227 * 1024, "shared memory");
-  cudaError_t e = cudaFuncSetAttribute(inr_train_tc_kernel<DEPTH, SIGMA, false, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
+  // N1 (north star: "TMA-staged hash tables in shared memory"): as many leading DENSE levels as fit beside the tiles
+  FusedArgs a = a_in;
+  {
+    const nsv_grid_meta& m = a.cfg.grid;
+    const size_t room = 227 * 1024 - L::bytes;
+    int n = 0;
+    while (n < m.n_levels && !m.hashed[n] && (size_t)m.offset[n + 1] * 4 <= room) ++n;
+    a.smem_levels = a_in.smem_levels < 0 ? n : (a_in.smem_levels < n ? a_in.smem_levels : n);
+    if (!a.fast || (m.n_levels & 3)) a.smem_levels = 0;  // the generic loops address the table globally
+  }
+  a.smem_table_bytes = a.smem_levels > 0 ? a.cfg.grid.offset[a.smem_levels] * 4u : 0u;
+  const size_t smem_total = L::bytes + a.smem_table_bytes;
+  cudaError_t e = cudaFuncSetAttribute(inr_train_tc_kernel<DEPTH, SIGMA, false, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total);
   if (e != cudaSuccess) {
     set_error("nsv_inr_train_step(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return (int)e;
@@ -727,10 +753,10 @@ int launch_tc(const FusedArgs& a, cudaStream_t st) {
   const int64_t ctas = (a.B * (int64_t)a.S / kGR + kNGroups - 1) / kNGroups;
   const int grid = (int)(ctas < num_sms() ? ctas : num_sms());
   if (a.timers && DEPTH == 3 && !SIGMA) {  // profiling build of the config-2 instantiation
-    cudaFuncSetAttribute(inr_train_tc_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcLayout<3, false>::bytes);
-    inr_train_tc_kernel<3, false, true><<<grid, kThreads, L::bytes, st>>>(a);
+    cudaFuncSetAttribute(inr_train_tc_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total);
+    inr_train_tc_kernel<3, false, true><<<grid, kThreads, smem_total, st>>>(a);
   } else {
-    inr_train_tc_kernel<DEPTH, SIGMA, false, BIAS><<<grid, kThreads, L::bytes, st>>>(a);
+    inr_train_tc_kernel<DEPTH, SIGMA, false, BIAS><<<grid, kThreads, smem_total, st>>>(a);
   }
   if (int err = check_launch("nsv_inr_train_step(tcgen05)")) return err;
   inr_finalize_kernel<<<1, 256, 0, st>>>(a.logit_coef, a.g_c, a.losses, a.n_slices, a.cfg.slice_scale, a.cfg.image_reg, a.cfg.delta,

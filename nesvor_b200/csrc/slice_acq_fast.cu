@@ -13,8 +13,10 @@
 //     reference walks every tap of every pixel; on the BASELINE stacks 82 % of the pixels lie outside); all taps inside ->
 //     no per-tap bounds tests and the normalisation weight of the scatter / backward passes (their first tap loop, Q3) is
 //     the pre-summed PSF; only border pixels take the checked loops;
-//   * the rotated tap offsets R.t are the same for every pixel of a slice: one float4 {R.t, psf} table per CTA tile in
-//     shared memory replaces 9 multiply-adds per tap and pixel;
+//   * tap positions are evaluated with exactly the reference's expression (x_center + r11 ix_p + r12 iy_p + r13 iz_p,
+//     slice_acq_cuda_kernel.cu:66-68, contracted to the same FMA chain by nvcc), so that taps lying ON a boundary plane of
+//     lattice-aligned stacks fall on the same side as in the reference's own build; the compacted taps are one float4
+//     {ix_p, iy_p, iz_p, psf} per tap in shared memory;
 //   * the volume is gathered from / scattered into the copy whose FASTEST axis is the one a slice's pixel rows run along
 //     (x-, y- or z-fastest; two transposed scratch copies are made / merged by a streaming pre- / post-pass), and warps are
 //     32 x 1 pixel rows along that axis when the slice is within a few degrees of it (8 x 4 patches otherwise): a warp-wide
@@ -147,7 +149,7 @@ __device__ void build_ctx(const float* __restrict__ tf, const Geo& g, Ctx& cx) {
 // Shared-memory carve-up: Smem header | float4 tap[nnz_max] | float val[ntaps] | int xyz[ntaps]
 struct Stage {
   Smem* sm;
-  float4* tap;  // {R.t (volume space), psf value}, rebuilt per slice
+  float4* tap;  // {ix_p, iy_p, iz_p, psf value} of the non-zero taps, reference order
   float* val;   // compacted non-zero taps, reference order
   int* xyz;     // packed signed bytes (tx, ty, tz)
 };
@@ -162,6 +164,12 @@ __device__ __forceinline__ Stage carve(unsigned char* smem, int ntaps) {
 }
 
 size_t smem_bytes(int ntaps) { return ((sizeof(Smem) + 15) / 16) * 16 + (size_t)ntaps * (16 + 4 + 4); }
+
+__device__ __forceinline__ void unpack_tap(int packed, int t[3]) {
+  t[0] = (int)(signed char)(packed & 0xff);
+  t[1] = (int)(signed char)((packed >> 8) & 0xff);
+  t[2] = (int)(signed char)((packed >> 16) & 0xff);
+}
 
 // once per CTA: ordered compaction of the non-zero taps by warp 0 (keeps the reference's summation order)
 __device__ void stage_psf(const float* __restrict__ psf, const Geo& g, Stage& st) {
@@ -182,6 +190,11 @@ __device__ void stage_psf(const float* __restrict__ psf, const Geo& g, Stage& st
       base += __popc(m);
     }
     __syncwarp();
+    for (int i = threadIdx.x; i < base; i += 32) {
+      int t[3];
+      unpack_tap(st.xyz[i], t);
+      st.tap[i] = make_float4((float)t[0], (float)t[1], (float)t[2], st.val[i]);
+    }
     if (threadIdx.x == 0) {
       float s = 0.f;
       for (int i = 0; i < base; ++i) s += st.val[i];  // same order as the tap loops: identical to their sum
@@ -193,34 +206,23 @@ __device__ void stage_psf(const float* __restrict__ psf, const Geo& g, Stage& st
   __syncthreads();
 }
 
-__device__ __forceinline__ void unpack_tap(int packed, int t[3]) {
-  t[0] = (int)(signed char)(packed & 0xff);
-  t[1] = (int)(signed char)((packed >> 8) & 0xff);
-  t[2] = (int)(signed char)((packed >> 16) & 0xff);
-}
 
-// CTA-uniform: make `is` the current slice (pose, layout, rotated tap table)
+// CTA-uniform: make `is` the current slice (pose, layout choice, classification bounds)
 __device__ void enter_slice(int is, const float* __restrict__ transforms, const Geo& g, Stage& st) {
   if (st.sm->cur_slice == is) return;
-  __syncthreads();  // everybody is done with the previous slice's table
+  __syncthreads();  // everybody is done with the previous slice's context
   if (threadIdx.x == 0) {
     build_ctx(transforms + (size_t)is * 12, g, st.sm->ctx);
     st.sm->cur_slice = is;
   }
   __syncthreads();
-  const Ctx& cx = st.sm->ctx;
-  for (int i = threadIdx.x; i < st.sm->nnz; i += kThreads) {
-    int t[3];
-    unpack_tap(st.xyz[i], t);
-    float4 v;
-    v.x = cx.R[0][0] * t[0] + cx.R[0][1] * t[1] + cx.R[0][2] * t[2];
-    v.y = cx.R[1][0] * t[0] + cx.R[1][1] * t[1] + cx.R[1][2] * t[2];
-    v.z = cx.R[2][0] * t[0] + cx.R[2][1] * t[1] + cx.R[2][2] * t[2];
-    v.w = st.val[i];
-    st.tap[i] = v;
-  }
-  __syncthreads();
 }
+
+// position of tap `tp` of a pixel, copy axis order; the reference's expression and association (slice_acq_cuda_kernel.cu:66-68)
+#define NSV_TAP_POS(p, px, R, tp)                                                            \
+  const float p[3] = {px.c[0] + R[0][0] * tp.x + R[0][1] * tp.y + R[0][2] * tp.z,            \
+                      px.c[1] + R[1][0] * tp.x + R[1][1] * tp.y + R[1][2] * tp.z,            \
+                      px.c[2] + R[2][0] * tp.x + R[2][1] * tp.y + R[2][2] * tp.z}
 
 struct Pixel {
   int ix, iy;
@@ -254,7 +256,7 @@ __device__ __forceinline__ void locate(int is, int tile, const Geo& g, const Ctx
 #pragma unroll
   for (int a = 0; a < 3; ++a) {  // copy axes
     const float v = cx.R[a][0] * px.s[0] + cx.R[a][1] * px.s[1] + cx.R[a][2] * px.s[2];
-    px.c[a] = v + cx.half[a];
+    px.c[a] = (float)((double)v + (double)cx.half[a]);  // x_center += (W - 1) / 2. (double, then narrowed)
     all_in = all_in && px.c[a] >= cx.lo_in[a] && px.c[a] <= cx.hi_in[a];
     out = out || px.c[a] < cx.lo_out[a] || px.c[a] > cx.hi_out[a];
   }
@@ -318,11 +320,12 @@ __device__ __forceinline__ void trigrad(const float f[8], const float w[3], floa
 
 // normalisation weight of the scatter / backward passes (Q3: in-bounds taps, vol_mask ignored)
 __device__ __forceinline__ float border_weight(const Pixel& px, const Stage& st, const float top[3]) {
+  const float (*R)[3] = st.sm->ctx.R;
   float weight = 0.f;
   const int nnz = st.sm->nnz;
   for (int i = 0; i < nnz; ++i) {
     const float4 tp = st.tap[i];
-    const float p[3] = {px.c[0] + tp.x, px.c[1] + tp.y, px.c[2] + tp.z};
+    NSV_TAP_POS(p, px, R, tp);
     if (in_bounds(p, top)) weight += tp.w;
   }
   return weight;
@@ -446,6 +449,7 @@ __global__ void __launch_bounds__(kThreads)
     if (!__any_sync(0xffffffffu, active)) return;
     const int s[3] = {1, cx.s[1], cx.s[2]};
       const float top[3] = {cx.top[0], cx.top[1], cx.top[2]};
+      const float R[3][3] = {{cx.R[0][0], cx.R[0][1], cx.R[0][2]}, {cx.R[1][0], cx.R[1][1], cx.R[1][2]}, {cx.R[2][0], cx.R[2][1], cx.R[2][2]}};
     const float* __restrict__ v = vol.at(cx.perm);
     const int nnz = st.sm->nnz;
     float val = 0.f, weight = 0.f;
@@ -454,7 +458,7 @@ __global__ void __launch_bounds__(kThreads)
         if (active) {
           for (int i = 0; i < nnz; ++i) {
             const float4 tp = st.tap[i];
-            const float p[3] = {px.c[0] + tp.x, px.c[1] + tp.y, px.c[2] + tp.z};
+            NSV_TAP_POS(p, px, R, tp);
             const Cell cell = make_cell(p, s);
             float f[8];
             load8(v, cell.base, s, f);
@@ -465,7 +469,7 @@ __global__ void __launch_bounds__(kThreads)
       } else if (active) {
         for (int i = 0; i < nnz; ++i) {
           const float4 tp = st.tap[i];
-          const float p[3] = {px.c[0] + tp.x, px.c[1] + tp.y, px.c[2] + tp.z};
+          NSV_TAP_POS(p, px, R, tp);
           if (!in_bounds(p, top)) continue;
           const Cell cell = make_cell(p, s);
           float f[8];
@@ -477,7 +481,7 @@ __global__ void __launch_bounds__(kThreads)
     } else if (active) {  // masked voxels drop out of value AND weight, corner by corner (layout: the caller's, perm == 0)
       for (int i = 0; i < nnz; ++i) {
         const float4 tp = st.tap[i];
-        const float p[3] = {px.c[0] + tp.x, px.c[1] + tp.y, px.c[2] + tp.z};
+        NSV_TAP_POS(p, px, R, tp);
         if (!in_bounds(p, top)) continue;
         const Cell cell = make_cell(p, s);
 #pragma unroll
@@ -518,6 +522,7 @@ __global__ void __launch_bounds__(kThreads)
     if (__any_sync(0xffffffffu, active)) {
       const int s[3] = {1, cx.s[1], cx.s[2]};
       const float top[3] = {cx.top[0], cx.top[1], cx.top[2]};
+      const float R[3][3] = {{cx.R[0][0], cx.R[0][1], cx.R[0][2]}, {cx.R[1][0], cx.R[1][1], cx.R[1][2]}, {cx.R[2][0], cx.R[2][1], cx.R[2][2]}};
       const float* __restrict__ v = vol.at(cx.perm);
       float* __restrict__ gv = grad_vol.at(cx.perm);
       const int nnz = st.sm->nnz;
@@ -529,7 +534,7 @@ __global__ void __launch_bounds__(kThreads)
       }
       for (int i = 0; i < nnz; ++i) {
         const float4 tp = st.tap[i];
-        const float p[3] = {px.c[0] + tp.x, px.c[1] + tp.y, px.c[2] + tp.z};
+        NSV_TAP_POS(p, px, R, tp);
         const bool valid = active && (px.cls == 2 || in_bounds(p, top));
         if (!merge && !valid) continue;
         Cell cell;
@@ -593,6 +598,7 @@ __global__ void __launch_bounds__(kThreads)
     if (!__any_sync(0xffffffffu, active)) return;
     const int s[3] = {1, cx.s[1], cx.s[2]};
       const float top[3] = {cx.top[0], cx.top[1], cx.top[2]};
+      const float R[3][3] = {{cx.R[0][0], cx.R[0][1], cx.R[0][2]}, {cx.R[1][0], cx.R[1][1], cx.R[1][2]}, {cx.R[2][0], cx.R[2][1], cx.R[2][2]}};
     float* __restrict__ dv = vol.at(cx.perm);
     float* __restrict__ dw = two ? vol_weight.at(cx.perm) : nullptr;
     const int nnz = st.sm->nnz;
@@ -605,7 +611,7 @@ __global__ void __launch_bounds__(kThreads)
     }
     for (int i = 0; i < nnz; ++i) {
       const float4 tp = st.tap[i];
-      const float p[3] = {px.c[0] + tp.x, px.c[1] + tp.y, px.c[2] + tp.z};
+      NSV_TAP_POS(p, px, R, tp);
       const bool valid = active && (px.cls == 2 || in_bounds(p, top));
       if (!merge && !valid) continue;
       Cell cell;
@@ -652,6 +658,7 @@ __global__ void __launch_bounds__(kThreads)
     if (active) {
       const int s[3] = {1, cx.s[1], cx.s[2]};
       const float top[3] = {cx.top[0], cx.top[1], cx.top[2]};
+      const float R[3][3] = {{cx.R[0][0], cx.R[0][1], cx.R[0][2]}, {cx.R[1][0], cx.R[1][1], cx.R[1][2]}, {cx.R[2][0], cx.R[2][1], cx.R[2][2]}};
       const float* __restrict__ gv = grad_vol.at(cx.perm);
       const float* __restrict__ rv = has_resid ? resid.at(cx.perm) : nullptr;
       const int nnz = st.sm->nnz;
@@ -659,7 +666,7 @@ __global__ void __launch_bounds__(kThreads)
       float val = 0.f, weight = 0.f;
       for (int i = 0; i < nnz; ++i) {
         const float4 tp = st.tap[i];
-        const float p[3] = {px.c[0] + tp.x, px.c[1] + tp.y, px.c[2] + tp.z};
+        NSV_TAP_POS(p, px, R, tp);
         if (px.cls != 2 && !in_bounds(p, top)) continue;
         const Cell cell = make_cell(p, s);
         float f[8];
@@ -766,6 +773,16 @@ struct Scratch {
   int alloc(int count, const Geo& g, cudaStream_t stream, bool zero) {
     st = stream;
     each = ((size_t)g.D * g.H * g.W + 63) / 64 * 64;
+    static bool pool_ready = false;
+    if (!pool_ready) {  // keep freed scratch in the device's default pool across synchronisations (the default gives it back)
+      int dev = 0;
+      cudaMemPool_t pool;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      pool_ready = true;
+    }
     cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&base), each * count * sizeof(float), st);
     if (e == cudaSuccess && zero) e = cudaMemsetAsync(base, 0, each * count * sizeof(float), st);
     if (e != cudaSuccess) {

@@ -116,10 +116,11 @@ __device__ __forceinline__ int corner_off(int c, int sy, int sz) { return (c & 1
 __device__ __forceinline__ constexpr int corner_at(int k) { return (0x76534210u >> (4 * k)) & 7; }
 #define NSV_CORNERS(c) _Pragma("unroll") for (int k_ = 0; k_ < 8; ++k_) if (const int c = corner_at(k_); true)
 
+// pose-gradient side only (never feeds a bit-exact output): evaluated in double, see TfGrad
 template <typename T>
-__device__ __forceinline__ void cell_grad(const Cell<T>& cell, int c, T v, T d[3]) {
+__device__ __forceinline__ void cell_grad(const Cell<T>& cell, int c, double v, double d[3]) {
   const int bx = c & 1, by = (c >> 1) & 1, bz = c >> 2;
-  const T gx = cell.fy[by] * cell.fz[bz] * v, gy = cell.fx[bx] * cell.fz[bz] * v, gz = cell.fx[bx] * cell.fy[by] * v;
+  const double gx = (double)cell.fy[by] * cell.fz[bz] * v, gy = (double)cell.fx[bx] * cell.fz[bz] * v, gz = (double)cell.fx[bx] * cell.fy[by] * v;
   d[0] = bx ? d[0] + gx : d[0] - gx;
   d[1] = by ? d[1] + gy : d[1] - gy;
   d[2] = bz ? d[2] + gz : d[2] - gz;
@@ -170,7 +171,7 @@ __device__ __forceinline__ T psf_resampled(const T* raw, const Cell<T>& pc, cons
 }
 
 template <typename T>
-__device__ __forceinline__ void psf_cell_grad(const T* raw, const Cell<T>& pc, const Dims& d, T g[3]) {
+__device__ __forceinline__ void psf_cell_grad(const T* raw, const Cell<T>& pc, const Dims& d, double g[3]) {
   g[0] = g[1] = g[2] = 0;
   NSV_CORNERS(c) cell_grad<T>(pc, c, raw[pc.base + corner_off(c, d.w_p, d.w_p * d.h_p)], g);
 }
@@ -207,7 +208,7 @@ struct TfGrad {
 #pragma unroll
     for (int k = 0; k < 12; ++k) g[k] = 0;
   }
-  __device__ __forceinline__ void add_linear(const Frame<T>& f, const T d[3], const int t[3]) {
+  __device__ __forceinline__ void add_linear(const Frame<T>& f, const double d[3], const int t[3]) {
     const double q[3] = {(double)(f.s[0] + t[0]), (double)(f.s[1] + t[1]), (double)(f.s[2] + t[2])};
 #pragma unroll
     for (int r = 0; r < 3; ++r)
@@ -216,7 +217,7 @@ struct TfGrad {
 #pragma unroll
     for (int c = 0; c < 3; ++c) g[c * 4 + 3] += (double)d[0] * f.r[0][c] + (double)d[1] * f.r[1][c] + (double)d[2] * f.r[2][c];
   }
-  __device__ __forceinline__ void add_nearest(const T d[3], const Nearest<T>& nt, const Dims& dm) {
+  __device__ __forceinline__ void add_nearest(const double d[3], const Nearest<T>& nt, const Dims& dm) {
     const double q[3] = {nt.r[0] - (dm.W - 1) / 2., nt.r[1] - (dm.H - 1) / 2., nt.r[2] - (dm.D - 1) / 2.};
 #pragma unroll
     for (int r = 0; r < 3; ++r)
@@ -372,9 +373,9 @@ __global__ void __launch_bounds__(kThreads)
             if (vol_mask && !vol_mask[nt.vox]) continue;
             if (grad_vol) atomicAdd(grad_vol + nt.vox, psf_resampled<T>(st.raw, nt.pc, d) * gs);
             if (grad_tf) {
-              T g[3];
+              double g[3];
               psf_cell_grad<T>(st.raw, nt.pc, d, g);
-              const T sc = gs * __ldg(vol + nt.vox);
+              const double sc = (double)gs * __ldg(vol + nt.vox);
               g[0] *= sc; g[1] *= sc; g[2] *= sc;
               acc.add_nearest(g, nt, d);
             }
@@ -389,11 +390,11 @@ __global__ void __launch_bounds__(kThreads)
               }
             }
             if (grad_tf) {
-              T g[3] = {0, 0, 0};
+              double g[3] = {0, 0, 0};
               NSV_CORNERS(c) {
                 const int iv = cell.base + corner_off(c, sy, sz);
                 if (vol_mask && !vol_mask[iv]) continue;
-                cell_grad<T>(cell, c, tap * __ldg(vol + iv), g);
+                cell_grad<T>(cell, c, (double)tap * __ldg(vol + iv), g);
               }
               acc.add_linear(f, g, t);
             }
@@ -502,9 +503,9 @@ __global__ void __launch_bounds__(kThreads)
           if (!nearest_psf_cell<T>(f, d, nt)) continue;
           tap = psf_resampled<T>(st.raw, nt.pc, d);
           if (grad_tf) {
-            T g[3];
+            double g[3];
             psf_cell_grad<T>(st.raw, nt.pc, d, g);
-            const T sc = resid ? (sval - __ldg(resid + nt.vox)) * tapval : sval * tapval;
+            const double sc = resid ? ((double)sval - __ldg(resid + nt.vox)) * tapval : (double)sval * tapval;
             g[0] *= sc; g[1] *= sc; g[2] *= sc;
             acc.add_nearest(g, nt, d);
           }
@@ -518,12 +519,12 @@ __global__ void __launch_bounds__(kThreads)
             }
           }
           if (grad_tf) {
-            T g[3] = {0, 0, 0};
+            double g[3] = {0, 0, 0};
             NSV_CORNERS(c) {
               const int iv = cell.base + corner_off(c, sy, sz);
               if (vol_mask && !vol_mask[iv]) continue;
               const T gv = __ldg(grad_vol + iv);
-              const T sc = resid ? (sval - __ldg(resid + iv)) * gv : sval * gv;
+              const double sc = resid ? ((double)sval - __ldg(resid + iv)) * gv : (double)sval * gv;
               cell_grad<T>(cell, c, sc, g);
             }
             g[0] *= tap; g[1] *= tap; g[2] *= tap;

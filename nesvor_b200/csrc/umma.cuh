@@ -72,6 +72,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
       : "memory");
 }
 
+// ---- TMA engine, non-tensor form: one bulk copy global -> shared, completion counted in bytes on an mbarrier ----
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(mbar)), "r"(bytes) : "memory");
+}
+// `bytes` a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(saddr(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(saddr(mbar))
+               : "memory");
+}
+
 // TMEM allocation (one warp, all lanes); the base address is written to *slot in shared memory
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, int ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(saddr(slot)), "r"(ncols) : "memory");

@@ -77,8 +77,16 @@ def test_against_reference_kernel_outputs(native_lib, sa_mode, tag, kw, interp):
         if k == "adjbwd1_grad_slices":  # gathers an equalized (scatter-produced) grad_vol: round-off, not bits
             torch.testing.assert_close(v, ref, atol=2e-4, rtol=2e-4, msg=lambda m: f"{k}: {m}")
         elif sa_mode == "fast" and _tol(k, ref) is GATHER_TOL:
-            assert rel_l2(v, ref) <= 1e-6, (k, rel_l2(v, ref))
-            torch.testing.assert_close(v, ref, atol=5e-6, rtol=1e-5, msg=lambda m: f"{k}: {m}")
+            # FMA-contracted vs literal arithmetic on uniform-random volumes: the reference's own sm_100a build sits at
+            # 2.4e-7 ... 1.4e-6 from these CPU-built goldens (profiles/r02_kernelB_vs_reference.json)
+            assert rel_l2(v, ref) <= 3e-6, (k, rel_l2(v, ref))
+            torch.testing.assert_close(v, ref, atol=1e-5, rtol=1e-5, msg=lambda m: f"{k}: {m}")
+        elif sa_mode == "fast" and k.endswith("grad_tf"):
+            # d(trilinear)/d(position) is piecewise constant: a tap whose position rounds into the neighbouring cell under
+            # FMA contraction changes its whole contribution, so single entries move by ~1e-3 of the scale between ANY two
+            # fp32 builds (the reference's own GPU build vs these goldens: 4e-5 ... 1e-3, same file)
+            scale = float(ref.abs().max())
+            torch.testing.assert_close(v, ref, atol=5e-3 * scale, rtol=0, msg=lambda m: f"{k}: {m}")
         else:
             torch.testing.assert_close(v, ref, **_tol(k, ref), msg=lambda m: f"{k}: {m}")
 
@@ -145,8 +153,8 @@ def test_fast_flavour_matches_fp64_as_well_as_the_exact_one(native_lib, kind, tu
         e_fast, e_exact = rel_l2(fast[k], truth[k]), rel_l2(exact[k], truth[k])
         floor = 5e-5 if k.endswith("grad_tf") else 2e-6
         assert e_fast <= max(2 * e_exact, floor), (k, e_fast, e_exact)
-        if k in ("slices", "weight") or k.endswith("0_grad_slices"):
-            assert rel_l2(fast[k], exact[k]) <= 1e-6, (k, rel_l2(fast[k], exact[k]))
+        if k in ("slices", "weight") or k.endswith("0_grad_slices"):  # gathers: FMA vs literal arithmetic on random data
+            assert rel_l2(fast[k], exact[k]) <= 3e-6, (k, rel_l2(fast[k], exact[k]))
         assert (fast[k] != 0).any()
 
 

@@ -17,15 +17,21 @@ pytestmark = pytest.mark.gpu
 
 
 def test_against_reference_cuda_extension_on_the_gpu(native_lib):
-    """Kernel B (the product's fast FMA build AND the bit-exact -fmad=false build) vs the reference's OWN CUDA extension
-    compiled for sm_100a (oracle/build_ref_gpu.sh: slice_acq_cuda.cpp + slice_acq_cuda_kernel.cu from /root/reference with the
-    one-token torch-2.x fix), same inputs, same GPU, all four operators, with and without masks
-    (tools/kernel_b_vs_reference.py, run in a subprocess so that a foreign kernel can never poison this process's CUDA
-    context).  Two fp32 implementations that sum thousands of terms in different orders (atomics, FMA contraction) differ
-    at round-off, and for an ill-conditioned output (the 12 pose-gradient sums) nobody can say a priori by how much: the
-    yardstick is the fp64 evaluation of the same operator (this library's _f64 entry points).  Bar: ours is at least as
-    close to fp64 as the reference's own kernel is (x2 for run-to-run atomic-order noise), or below an absolute round-off
-    floor.  Skipped when the prebuilt extension is absent or cannot be loaded / called on this box."""
+    """Kernel B vs the reference's OWN CUDA extension compiled for sm_100a (oracle/build_ref_gpu.sh: slice_acq_cuda.cpp +
+    slice_acq_cuda_kernel.cu from /root/reference with the one-token torch-2.x fix), same inputs, same GPU, all four
+    operators, with and without masks (tools/kernel_b_vs_reference.py, run in a subprocess so that a foreign kernel can
+    never poison this process's CUDA context).
+
+    * Product (fast) flavour: evaluates tap positions with the reference's own expression under the same FMA contraction,
+      so it must REPRODUCE the reference's GPU results: gathers <= 2e-6, scatter passes <= 5e-6 (float-atomic order),
+      pose gradients <= 5e-5 relative L2.
+    * Bit-exact flavour (-fmad=false == the reference compiled for the CPU, pinned bit for bit by the golden tests): the
+      fp64 evaluation of the same operator (this library's _f64 entry points) is the yardstick -- at least as close to fp64
+      as the reference's GPU build is (x2), or below a round-off floor.  The pose gradient is a sum of piecewise-constant
+      d(trilinear)/d(position) terms: a tap whose position rounds into the neighbouring cell changes its whole term, so two
+      correct fp32 builds with different contraction differ by ~1e-3 there (measured: reference GPU 3.0e-4, literal
+      arithmetic 1.1e-3 from fp64 on the same case); floor 2e-3.
+    Skipped when the prebuilt extension is absent or cannot be loaded / called on this box."""
     import json
     import subprocess
     import sys
@@ -41,10 +47,15 @@ def test_against_reference_cuda_extension_on_the_gpu(native_lib):
         if not out.get("available"):
             pytest.skip("reference CUDA extension not available: " + str(out.get("why")))
         print(line)
-        for case, errs in out["err_vs_f64"].items():
-            for k, e in errs.items():
-                floor = 5e-5 if k.endswith("grad_tf") else (2e-6 if k in ("slices", "weight") or k.endswith("grad_slices") else 5e-6)
-                assert e["ours"] <= max(2.0 * e["reference"], floor), (exact, case, k, e)
+        for case in ("plain", "masked"):
+            for k, e in out["err_vs_f64"][case].items():
+                gather = k in ("slices", "weight") or k.endswith("grad_slices")
+                if exact:
+                    floor = 2e-3 if k.endswith("grad_tf") else (2e-6 if gather else 5e-6)
+                    assert e["ours"] <= max(2.0 * e["reference"], floor), (exact, case, k, e)
+                else:
+                    d = out["rel_l2"][case][k]
+                    assert d <= (5e-5 if k.endswith("grad_tf") else (2e-6 if gather and not k.startswith("adjbwd1") else 5e-6)), (case, k, d)
         for k, err in out["rel_l2"]["pose_converters"].items():
             # same formulas, FMA-contracted vs literal arithmetic; the backward passes divide by sin / theta
             assert err <= (1e-5 if k.endswith("fwd") else 1e-3), (k, err)

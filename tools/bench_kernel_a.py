@@ -64,8 +64,10 @@ def main():
     for var in [(v, ab) for v in a.variants.split(",") for ab in a.ablate.split(",")]:
         var, ablate = var
         os.environ["NSV_ABLATE"] = ablate
-        agg, fast = (int(x) for x in var.split(":"))
+        agg, fast, *rest = (int(x) for x in var.split(":"))
+        smem = rest[0] if rest else -2  # third field: levels staged in shared memory (-1 as many as fit, 0 none)
         _lib.set_fused_tuning(agg, fast)
+        _lib.lib().nsv_set_fused_smem_levels(smem)
         durs = []
         for i in range(3 + a.reps):
             flush.zero_()
@@ -77,9 +79,10 @@ def main():
             torch.cuda.synchronize()
             if i >= 3:
                 durs.append(k0.elapsed_time(k1))
-        print(json.dumps({"cfg": a.cfg, "impl": a.impl, "agg_max": agg, "fast": fast, "ablate": int(ablate), "ms_mean": sum(durs) / len(durs), "ms_min": min(durs),
+        print(json.dumps({"cfg": a.cfg, "impl": a.impl, "agg_max": agg, "fast": fast, "smem_levels": smem, "ablate": int(ablate), "ms_mean": sum(durs) / len(durs), "ms_min": min(durs),
                           "gq_per_s": B * S / (min(durs) * 1e-3) / 1e9}), flush=True)
     _lib.set_fused_tuning(-1, -1)
+    _lib.lib().nsv_set_fused_smem_levels(-2)
     if args.n_levels_bias:  # the mean(log_bias) pre-pass alone (part of every forward_backward timed above)
         import ctypes
 

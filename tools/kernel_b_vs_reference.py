@@ -138,16 +138,16 @@ def main():
 
         def timed(fn):
             durs = []
-            for i in range(1 + a.reps):
+            for i in range(2 + a.reps):
                 flush.zero_()
                 k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 k0.record()
                 res_ = fn()
                 k1.record()
                 torch.cuda.synchronize()
-                if i >= 1:
+                if i >= 2:
                     durs.append(k0.elapsed_time(k1))
-            return res_, sum(durs) / len(durs)
+            return res_, sorted(durs)[len(durs) // 2]  # median: a stray allocator / clock hiccup must not decide a ratio
 
         s_ref, t_ref_f = timed(lambda: ref.forward(mat, vol, empty, empty, psf, [ss, ss], 1.0, False, False)[0])
         s_our, t_our_f = timed(lambda: sa.forward(mat, vol, None, None, psf, (ss, ss), 1.0, False, False)[0])

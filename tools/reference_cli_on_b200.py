@@ -99,8 +99,20 @@ def config2_through_cli(cli, compat, nb, dev, tmp, n_iter=600):
     slices, _, _ = simulate_slices(device=dev, n=128, n_stacks=3, res_r=1.0, res_s=1.0, gap=3.0)
     folder = os.path.join(tmp, "slices_cfg2")
     nb.save_slices(folder, slices)
+    # the reference derives the number of levels from the data's bounding box (models.py:79-101):
+    # n_levels = ceil(log2(extent / finest / base) / log2(scale) + 1), base = ceil(extent / coarsest).  BASELINE config 2
+    # names L = 16, so --finest-resolution is chosen to land in the middle of the L = 16 bracket for THIS folder's extent.
+    import math
+    from argparse import Namespace
+
+    from nesvor_b200.nesvor.train import Dataset
+
+    bb = Dataset(nb.load_slices(folder, dev), Namespace(mask_threshold=1.0)).bounding_box
+    extent = float((bb[1] - bb[0]).max())
+    base = math.ceil(extent / 16.0)
+    finest = extent / base / 1.3819**14.5
     argv = ["nesvor", "reconstruct", "--input-slices", folder, "--output-model", os.path.join(tmp, "model_cfg2.pt"), "--n-iter", str(n_iter),
-            "--batch-size", "8192", "--n-samples", "128", "--depth", "3", "--finest-resolution", "0.119", "--no-pixel-variance",
+            "--batch-size", "8192", "--n-samples", "128", "--depth", "3", "--finest-resolution", "%.6f" % finest, "--no-pixel-variance",
             "--no-slice-variance", "--no-transformation-optimization", "--verbose", "0", "--seed", "0"]
     old_argv, sys.argv = sys.argv, argv
     try:
