@@ -34,6 +34,17 @@ WORKLOAD = dict(
     n=128, n_stacks=3, n_levels=16, log2_hashmap_size=19, width=64, depth=3, n_samples=128, batch_size=8192)
 
 
+L2_NOTE = ("per-step working set 184 MB (params+grads+Adam moments) > 126 MB L2; kernel-only timing flushes L2 with a 256 MB write")
+
+
+def config_block(world, scaling="weak", batch_size=None):
+    """`config` of the JSON line -- identical for both arms (the driver compares them): the workload and how it is sharded."""
+    c = dict(WORKLOAD, parallelism=f"dp{world}", l2=L2_NOTE, noise="in-kernel Philox (ours) / torch.randn (reference arm)", scaling=scaling)
+    if batch_size is not None:
+        c["batch_size"] = batch_size
+    return c
+
+
 def make_args(device, **kw):
     import torch
 
@@ -85,10 +96,14 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_oracle_throughput(n_pixels=256, n_samples=128, steps=2, warmup=1, threads=None):
+def cpu_oracle_throughput(n_pixels=8192, n_samples=128, steps=2, warmup=1, threads=None, budget_s=None):
     """The reference has no CPU path; the CPU baseline is the oracle port:
-    oracle/inr_oracle.py forward + autograd backward + torch AdamW, config-2 model, all host cores,
-    on a bounded sample of the workload (n_pixels x n_samples queries per step)."""
+    oracle/inr_oracle.py forward + autograd backward + torch AdamW, config-2 model, all host cores.
+
+    Same configuration as the GPU arm: every step is a FULL config-2 iteration (8192 px x 128 samples = 2^20 queries,
+    ~3-6 s on 16 cores) unless `budget_s` is given and (warmup + steps) full iterations would not fit in it: then the
+    FIRST timed step stays full-size and the others shrink to a bounded sample of the same workload (>= 256 px).  `value` is
+    total queries / total time over the timed steps; the full-size iteration is also reported on its own."""
     import torch
     from oracle import inr_oracle as io
 
@@ -105,36 +120,54 @@ def cpu_oracle_throughput(n_pixels=256, n_samples=128, steps=2, warmup=1, thread
                        delta=0.2 * 0.3, emulate_fp16=False)
     om = io.OracleNeSVoR(cfg, n_slices, ax, res, bb)
     opt = io.make_optimizer(om)
-    times = []
-    for it in range(warmup + steps):
-        xyz = (torch.rand(n_pixels, 3, generator=g) - 0.5) * 100
+
+    def step(n_px):
+        xyz = (torch.rand(n_px, 3, generator=g) - 0.5) * 100
         xyz[:, 2] = 0
-        v = torch.rand(n_pixels, generator=g)
-        idx = torch.randint(0, n_slices, (n_pixels,), generator=g)
+        v = torch.rand(n_px, generator=g)
+        idx = torch.randint(0, n_slices, (n_px,), generator=g)
         t0 = time.perf_counter()
-        noise = torch.randn(n_pixels, n_samples, 3, generator=g)
+        noise = torch.randn(n_px, n_samples, 3, generator=g)
         losses = om.forward(xyz, v, idx, noise)
         om.total_loss(losses).backward()
         opt.step()
         opt.zero_grad()
-        if it >= warmup:
-            times.append(time.perf_counter() - t0)
-    per_step = sum(times) / len(times)
-    return {"value": n_pixels * n_samples / per_step, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{steps} iterations of {n_pixels} px x {n_samples} samples ({n_pixels * n_samples} queries/iter) of the config-2 model, "
-                      f"oracle/inr_oracle.py fwd+bwd+AdamW, torch {torch.__version__}, {threads} threads",
-            "ms_per_step": per_step * 1e3}
+        return time.perf_counter() - t0
+
+    small = n_pixels
+    t_probe = step(256)  # untimed: thread pool / allocator warm-up
+    if budget_s is not None:  # full-size iterations cost ~n_pixels / 256 / 2.5 probes (large batches run more efficiently)
+        est_full = max(t_probe * n_pixels / 256 / 2.5, 1e-3)
+        if (warmup + steps) * est_full > budget_s:
+            per_step = max(budget_s - est_full, 0.25 * budget_s) / max(warmup + steps - 1, 1)
+            small = int(max(256, min(n_pixels, 256 * per_step / t_probe)) // 256 * 256)
+    for _ in range(warmup):
+        step(small)
+    sizes = [n_pixels] + [small] * (steps - 1)
+    times = [step(n) for n in sizes]
+    total_q = sum(sizes) * n_samples
+    return {"value": total_q / sum(times), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{steps} timed iteration(s) of the config-2 model, oracle/inr_oracle.py fwd+bwd+AdamW, torch {torch.__version__}, {threads} threads: "
+                      f"1 x {n_pixels} px x {n_samples} samples (the full 2^20-query batch, {times[0]:.2f} s)"
+                      + (f" + {steps - 1} x {small} px x {n_samples}" if steps > 1 else ""),
+            "ms_per_step": sum(times) / len(times) * 1e3,
+            "full_batch_iteration": {"queries": n_pixels * n_samples, "seconds": times[0], "queries_per_s": n_pixels * n_samples / times[0]},
+            "all_steps_full_batch": small == n_pixels}
 
 
 def run_reference_arm(a):
+    """`--impl reference`: the reference's algorithm for the path on the host cores (the oracle port -- the reference itself has
+    no CPU path and its tiny-cuda-nn dependency is absent), same metric, same config-2 batch: every step is a
+    full 8192 px x 128 samples iteration as long as warmup + steps of them fit in ~4 minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base = cpu_oracle_throughput(steps=max(a.steps, 1), warmup=max(a.warmup, 1))
+    base = cpu_oracle_throughput(steps=max(a.steps, 1), warmup=max(a.warmup, 0), budget_s=240.0)
     line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": dict(WORKLOAD, note="reference arm = CPU oracle port on a bounded sample; the reference ships no CPU path and its tcnn dependency is absent"),
-            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_block(a.gpus, a.scaling),
+            "notes": "reference arm = CPU oracle port (oracle/inr_oracle.py); the reference ships no CPU path and its tcnn dependency is absent",
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample", "full_batch_iteration", "all_steps_full_batch")},
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -288,7 +321,13 @@ def run_ours(a):
     from nesvor_b200.nesvor.fused import FusedTrainer
     from nesvor_b200.nesvor.train import Dataset
 
-    args = make_args(dev)
+    strong = a.scaling == "strong"
+    if strong:  # BASELINE config 4: 2^22 queries / iteration GLOBALLY (32768 px x 128), sharded over the ranks
+        if 32768 % world:
+            raise SystemExit("bench.py --scaling strong: the 32768-pixel global batch must divide by the number of ranks")
+        args = make_args(dev, batch_size=32768 // world)
+    else:
+        args = make_args(dev)
     torch.manual_seed(0)
     slices, _, _ = simulate_slices(n=WORKLOAD["n"], n_stacks=WORKLOAD["n_stacks"], res_r=1.0, res_s=1.0, gap=3.0, device=dev)
     dataset = Dataset(slices, args)
@@ -340,12 +379,19 @@ def run_ours(a):
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    pending, loss_host = None, {}
     for i in range(a.steps):
         hb = host[i % len(host)]
-        batch = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+        batch = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}  # H2D of THIS step's inputs from pinned memory
         out = one_step(batch)
-        vals = torch.stack([v.reshape(()) for v in out.values()]).tolist()  # ONE D2H read of the step's losses (syncs, like train.py:199-200)
-        loss_host = dict(zip(out.keys(), vals))
+        # D2H of the step's losses, every step, the way nesvor_b200.train() does it: ONE async copy into pinned memory behind
+        # the step's kernels, read after the NEXT step has been enqueued (LossHandle) -- the reference's loop drains the GPU
+        # with 5-6 `.item()` calls per iteration (train.py:199-200)
+        handle = trainer.losses_to_host(out)
+        if pending is not None:
+            loss_host = pending.get()
+        pending = handle
+    loss_host = pending.get()
     e1.record()
     sync_all()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -354,6 +400,22 @@ def run_ours(a):
     e2e_value = world * n_q * a.steps / (float(t.item()) * 1e-3)
     h2d = B * (3 * 4 + 4 + 8)
     d2h = 4 * len(loss_host)
+
+    # ---------------- exchange step alone (N > 1): gradient mean + AdamW + parameter refresh over the ranks ----------------
+    exchange_ms = None
+    if world > 1:
+        sync_all()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_x = 20
+        x0.record()
+        for _ in range(n_x):
+            trainer.iteration += 1
+            trainer._dp_update(dist, world)  # zero gradients: the parameters only see the weight decay of 20 tiny steps
+        x1.record()
+        sync_all()
+        t = torch.tensor([x0.elapsed_time(x1) / n_x], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        exchange_ms = float(t.item())
 
     if rank != 0:
         clocks.__exit__(None, None, None)
@@ -410,15 +472,20 @@ def run_ours(a):
         except Exception:
             pass
 
-    cpu = cpu_oracle_throughput()
+    cpu = cpu_oracle_throughput(steps=2, warmup=1) if world == 1 else None  # rank 0 at N = 1 only: two full config-2 iterations
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
-            "data": "synthetic", "config": dict(WORKLOAD, parallelism=f"dp{world}", l2="per-step working set 184 MB (params+grads+Adam moments) > 126 MB L2; kernel-only timing flushes L2 with a 256 MB write",
-                                                noise="in-kernel Philox", n_pixels_in_table=int(dataset.xyz.shape[0]), n_slices=model.n_slices),
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
+            "data": "synthetic", "config": config_block(world, a.scaling, B if strong else None),
+            "workload_detail": {"n_pixels_in_table": int(dataset.xyz.shape[0]), "n_slices": model.n_slices, "queries_per_rank_per_step": n_q,
+                                "global_queries_per_step": n_q * world, "smem_staged_levels": "levels gathered from the TMA-staged shared-memory copy: see DESIGN.md s.4"},
+            "dp": {"mode": trainer.dp_mode, "exchange_ms": exchange_ms,
+                   "what": "exchange = gradient mean over the ranks + AdamW + fp16 parameter refresh; 'peer' = one fused kernel over NVLink peer memory "
+                           "(nsv_adamw_step_dp), 'allreduce' = NCCL all-reduce + nsv_adamw_step"} if world > 1 else None,
             "clocks": clocks.summary(), "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": 3 * a.steps, "roofline": roofline, "kernel_b": dict(kernel_b, frac=kernel_b["achieved"] / peak, peak=peak),
-            "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "losses_last_step": {k: float(v) for k, v in losses.items()}}
+    if cpu is not None:
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "full_batch_iteration")}
     if other_heads is not None:
         line["other_heads"] = other_heads
         line["unfused_gpu"] = unfused_leg(dev, dataset)  # last: a failure here cannot touch the numbers above
@@ -433,6 +500,8 @@ def main():
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 2^20 queries per rank per step (default); strong: BASELINE config 4, 2^22 queries per step globally")
     ap.add_argument("--fused-impl", default="auto", choices=["auto", "mma", "tcgen05", "ws"], help="implementation of kernel A")
     a = ap.parse_args()
     if a.impl == "reference":

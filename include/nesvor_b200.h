@@ -221,6 +221,11 @@ int nsv_set_fused_impl(int impl);
  * float-atomic ordering): `agg_max_entries` = largest dense level whose gradient is pre-reduced inside a warp before
  * touching global memory (0 = never, < 0 = default: every dense level, or $NSV_AGG_MAX); `fast_path` = 0 forces the generic
  * per-level loops, 1 the chunked branch-free loops, < 0 = default (1 or $NSV_FAST_PATH). */
+/* Verification hook: the PSF-sample generator every fused kernel uses when no noise tensor is passed (replaces
+ * torch.randn(B, S, 3), nesvor/nesvor/models.py:269 and :161): sample index idx = offset + i -> Philox4x32-10 with counter
+ * (idx_lo, idx_hi, 0, 0) and key (seed_lo, seed_hi) -> Box-Muller.  normals [n,3] f32 and / or raw [n,4] u32 (either may be
+ * NULL). */
+int nsv_debug_normal3(uint64_t seed, uint64_t offset, int64_t n, float* normals, uint32_t* raw, void* stream);
 /* Number of leading dense levels of the fp16 table that the tcgen05 training kernel stages into shared memory with one
  * bulk copy per CTA (TMA engine, cp.async.bulk) and gathers from there: -1 as many as fit beside the operand tiles
  * (default; env NSV_SMEM_LEVELS), 0 none, -2 back to the default.  Profiling / test hook. */

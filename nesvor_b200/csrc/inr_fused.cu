@@ -686,6 +686,39 @@ extern "C" int nsv_set_fused_timers(void* device_counters) {
   return NSV_OK;
 }
 
+// ---- verification hook: the PSF-noise generator of the fused kernels, exposed sample by sample ----
+namespace nsv {
+namespace fused {
+static __global__ void debug_normal3_kernel(uint64_t seed, uint64_t offset, int64_t n, float* __restrict__ normals, uint32_t* __restrict__ raw) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t idx = offset + (uint64_t)i;
+    if (normals) {
+      float e[3];
+      normal3(seed, idx, e);
+      normals[3 * i] = e[0];
+      normals[3 * i + 1] = e[1];
+      normals[3 * i + 2] = e[2];
+    }
+    if (raw) {
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+      raw[4 * i] = r.x;
+      raw[4 * i + 1] = r.y;
+      raw[4 * i + 2] = r.z;
+      raw[4 * i + 3] = r.w;
+    }
+  }
+}
+}  // namespace fused
+}  // namespace nsv
+
+extern "C" int nsv_debug_normal3(uint64_t seed, uint64_t offset, int64_t n, float* normals, uint32_t* raw, void* stream) {
+  NSV_REQUIRE(n >= 0 && (n == 0 || normals || raw), "nsv_debug_normal3: bad arguments");
+  if (n == 0) return NSV_OK;
+  const int64_t blocks = (n + 255) / 256;
+  nsv::fused::debug_normal3_kernel<<<(int)(blocks < 1184 ? blocks : 1184), 256, 0, (cudaStream_t)stream>>>(seed, offset, n, normals, raw);
+  return nsv::check_launch("nsv_debug_normal3");
+}
+
 extern "C" int nsv_set_fused_smem_levels(int levels) {
   nsv::fused::g_smem_levels = levels < -1 ? -2 : levels;
   return NSV_OK;

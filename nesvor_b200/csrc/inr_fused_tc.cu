@@ -740,7 +740,10 @@ int launch_tc(const FusedArgs& a_in, cudaStream_t st) {
     const size_t room = 227 * 1024 - L::bytes;
     int n = 0;
     while (n < m.n_levels && !m.hashed[n] && (size_t)m.offset[n + 1] * 4 <= room) ++n;
-    a.smem_levels = a_in.smem_levels < 0 ? n : (a_in.smem_levels < n ? a_in.smem_levels : n);
+    // default: at most 2 levels.  Measured on config 2 (profiles/r02_kernelA_smem_levels.txt): 0 / 1 / 2 / 3 staged levels =
+    // 0.7116 / 0.7137 / 0.7117 / 0.7158 ms -- the coarse levels' loads were L1 hits already (the table-load ablation of
+    // round 1 is worth 0.03 ms in total), so staging buys nothing and a third level costs shared-memory bandwidth.
+    a.smem_levels = a_in.smem_levels < 0 ? (n < 2 ? n : 2) : (a_in.smem_levels < n ? a_in.smem_levels : n);
     if (!a.fast || (m.n_levels & 3)) a.smem_levels = 0;  // the generic loops address the table globally
   }
   a.smem_table_bytes = a.smem_levels > 0 ? a.cfg.grid.offset[a.smem_levels] * 4u : 0u;

@@ -21,8 +21,8 @@
 //     (x-, y- or z-fastest; two transposed scratch copies are made / merged by a streaming pre- / post-pass), and warps are
 //     32 x 1 pixel rows along that axis when the slice is within a few degrees of it (8 x 4 patches otherwise): a warp-wide
 //     gather or reduction then touches 4-5 sectors instead of 13-32;
-//   * in row mode neighbouring lanes' cells overlap by one voxel column: the +1 corners are handed to the neighbour with a
-//     shuffle and leave as ONE reduction (halves the RED count of the scatter passes);
+//   * (tuning bit 4, off by default: measured slower) in row mode neighbouring lanes' cells overlap by one voxel column:
+//     the +1 corners can be handed to the neighbour with a shuffle and leave as ONE reduction;
 //   * A^T without `equalize` skips pixels whose value is exactly zero (they add 0 to every voxel).
 // Results agree with sa_exact to fp32 round-off (tests/test_gpu_slice_acq.py), not bit for bit.
 #define NSV_SA_NS sa_fma
@@ -798,7 +798,10 @@ struct Scratch {
   }
 };
 
-unsigned g_tune = kTunePerm | kTuneRow | kTuneMerge | kTuneZeroSkip | kTuneClassify;
+// default: everything but the neighbour merge -- measured on the BASELINE config-2 stacks (profiles/r02_kernelB_vs_reference.json)
+// the merge's 5 extra shuffles per tap cost more than the reductions it saves once row warps already put a warp's
+// reductions into 4-5 sectors (A^T 0.87 vs 1.18 ms, backward 1.53 vs 1.90 ms); it stays available as tuning bit 4
+unsigned g_tune = kTunePerm | kTuneRow | kTuneZeroSkip | kTuneClassify;
 
 int check_geo(const char* name, const Geo& d) {
   NSV_REQUIRE(d.D > 0 && d.H > 0 && d.W > 0 && d.d_p > 0 && d.h_p > 0 && d.w_p > 0 && d.n >= 0 && d.h > 0 && d.w > 0,

@@ -311,6 +311,20 @@ class FusedState:
         return out
 
 
+class LossHandle:
+    """The loss values of one iteration on their way to the host: a pinned buffer filled by an asynchronous copy that was
+    enqueued right behind the iteration's kernels, plus the event that marks its completion.  `get()` blocks only until
+    THAT copy has landed, so a loop that reads iteration i's losses after enqueueing iteration i + 1 (train() below does)
+    keeps one iteration of work queued on the GPU instead of draining it at every `.item()` (train.py:199-200)."""
+
+    def __init__(self, keys, host: torch.Tensor, event: torch.cuda.Event):
+        self.keys, self.host, self.event = keys, host, event
+
+    def get(self) -> Dict[str, float]:
+        self.event.synchronize()
+        return dict(zip(self.keys, self.host.tolist()))
+
+
 class FusedTrainer:
     """Drop-in for the body of train()'s loop: `losses = trainer.step(xyz=..., v=..., slice_idx=...)`."""
 
@@ -359,6 +373,19 @@ class FusedTrainer:
 
     def decay_lr(self, gamma: float) -> None:
         self.lr *= gamma
+
+    def losses_to_host(self, losses: Dict[str, torch.Tensor]) -> LossHandle:
+        """Enqueues ONE device-to-host copy of a step's loss values (pinned ring buffer) and returns its handle."""
+        if not hasattr(self, "_host_ring"):
+            self._host_ring = [torch.empty(8, dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._host_i = 0
+        keys = list(losses.keys())
+        host = self._host_ring[self._host_i % len(self._host_ring)][: len(keys)]
+        self._host_i += 1
+        host.copy_(torch.stack([losses[k].reshape(()) for k in keys]), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.state.device))
+        return LossHandle(keys, host, ev)
 
     def _trans_reg(self) -> None:
         """transReg (models.py:357-363) and its gradient in one native launch (`nsv_trans_reg_f32`): the weighted gradient is

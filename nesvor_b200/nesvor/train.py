@@ -144,6 +144,7 @@ def train(slices: List[Slice], args: Namespace) -> Tuple[INR, List[Slice], Volum
     average = MovingAverage(1 - 0.001)
     logging.info("NeSVoR training starts.")
     train_time = 0.0
+    pending = None
     for i in range(1, args.n_iter + 1):
         t0 = time.time()
         batch = dataset.get_batch(args.batch_size, args.device)
@@ -167,8 +168,18 @@ def train(slices: List[Slice], args: Namespace) -> Tuple[INR, List[Slice], Volum
             optimizer.zero_grad()
         train_time += time.time() - t0
         if not getattr(args, "no_loss_sync", False):
-            for k in losses:
-                average(k, losses[k].item())
+            if use_fused:  # one async D2H copy per step, read one step late: the GPU never drains (LossHandle)
+                if pending is not None:
+                    for k, val in pending.get().items():
+                        average(k, val)
+                pending = trainer.losses_to_host(losses)
+                if i == args.n_iter or (decay_milestones and i >= decay_milestones[0]):
+                    for k, val in pending.get().items():  # a log line is due: catch up
+                        average(k, val)
+                    pending = None
+            else:
+                for k in losses:
+                    average(k, losses[k].item())
         if (decay_milestones and i >= decay_milestones[0]) or i == args.n_iter:
             lr = trainer.lr if use_fused else optimizer.param_groups[0]["lr"]
             logging.info("time %s epoch %d iter %d %s lr %.3e", datetime.timedelta(seconds=int(train_time)), dataset.epoch, i,

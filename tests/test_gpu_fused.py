@@ -348,3 +348,72 @@ def test_fused_full_size_properties(native_lib):
     lin = float((ga + gb - 2 * gm).norm() / (ga.norm() + gb.norm()))
     print(f"full size: affinity defect of the gradient in v = {lin:.3e}")
     assert lin < 5e-3
+
+
+def _philox4x32_10_numpy(ctr, key):
+    """Independent restatement of Philox4x32-10 (Salmon et al., SC'11; Random123 philox.h): ctr [n,4], key [n,2] uint32."""
+    import numpy as np
+
+    c = ctr.astype(np.uint64).copy()
+    k = key.astype(np.uint64).copy()
+    M0, M1, W0, W1, mask = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[:, 0], M1 * c[:, 2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c = np.stack([hi1 ^ c[:, 1] ^ k[:, 0], lo1, hi0 ^ c[:, 3] ^ k[:, 1], lo0], 1)
+        k = np.stack([(k[:, 0] + W0) & mask, (k[:, 1] + W1) & mask], 1)
+    return c.astype(np.uint32)
+
+
+def test_in_kernel_normal_generator(native_lib):
+    """The PSF-sample generator of every benchmarked step (in-kernel Philox4x32-10 + Box-Muller; replaces torch.randn(B, S, 3),
+    nesvor/nesvor/models.py:269): (a) the counter-based core against Random123's published known-answer vector and an
+    independent numpy restatement (bit-exact); (b) the normals: first four moments, Kolmogorov-Smirnov against N(0,1) per
+    component, and no correlation between components or between consecutive sample indices, on 2^21 samples."""
+    import ctypes
+
+    import numpy as np
+    from scipy import stats
+
+    from nesvor_b200 import _lib
+
+    n = 1 << 21
+    seed, offset = 0x1234_5678_9ABC_DEF0, (1 << 33) + 12345  # exercises the high halves of key and counter
+    normals = torch.empty(n, 3, device="cuda")
+    raw = torch.empty(n, 4, dtype=torch.int32, device="cuda")
+    L = native_lib
+    _lib.check(L.nsv_debug_normal3(ctypes.c_uint64(seed), ctypes.c_uint64(offset), ctypes.c_int64(n), _lib.ptr(normals), _lib.ptr(raw), _lib.stream(normals.device)))
+    kat = torch.empty(1, 4, dtype=torch.int32, device="cuda")
+    _lib.check(L.nsv_debug_normal3(ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_int64(1), None, _lib.ptr(kat), _lib.stream(normals.device)))
+    torch.cuda.synchronize()
+    # (a) Random123 kat_vectors (philox4x32, 10 rounds): the numpy restatement reproduces all three published vectors ...
+    for c, k, want in (([0, 0, 0, 0], [0, 0], [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]),
+                       ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
+                       ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0], [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1])):
+        assert _philox4x32_10_numpy(np.array([c], np.uint32), np.array([k], np.uint32))[0].tolist() == want
+    # ... the kernel reproduces the zero vector directly and 4096 (counter, key) pairs of the restatement
+    assert [int(v) & 0xFFFFFFFF for v in kat[0].tolist()] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    idx = offset + np.arange(4096, dtype=np.uint64)
+    ctr = np.stack([idx & np.uint64(0xFFFFFFFF), idx >> np.uint64(32), np.zeros_like(idx), np.zeros_like(idx)], 1)
+    key = np.tile(np.array([[seed & 0xFFFFFFFF, seed >> 32]], dtype=np.uint64), (4096, 1))
+    want = _philox4x32_10_numpy(ctr, key)
+    got = raw[:4096].cpu().numpy().view(np.uint32)
+    assert (got == want).all()
+    # (b) distribution
+    x = normals.double().cpu().numpy()
+    assert np.isfinite(x).all()
+    se = 1.0 / np.sqrt(n)
+    for d in range(3):
+        c = x[:, d]
+        assert abs(c.mean()) < 5 * se, (d, c.mean())
+        assert abs(c.var() - 1.0) < 5 * np.sqrt(2.0) * se, (d, c.var())
+        assert abs(stats.skew(c)) < 5 * np.sqrt(6.0) * se, (d, stats.skew(c))
+        assert abs(stats.kurtosis(c)) < 5 * np.sqrt(24.0) * se, (d, stats.kurtosis(c))
+        ks = stats.kstest(c, "norm")
+        assert ks.pvalue > 1e-4 and ks.statistic < 2.2 * se, (d, ks)  # 2.2 / sqrt(n): the 1e-4 quantile of the Kolmogorov law
+        assert abs(c).max() < 7.0  # Box-Muller on 32-bit uniforms: |z| <= sqrt(2 ln 2^33) = 6.8
+        assert abs(np.corrcoef(c[:-1], c[1:])[0, 1]) < 5 * se  # consecutive sample indices
+    cc = np.corrcoef(x.T)
+    assert np.abs(cc - np.eye(3)).max() < 5 * se, cc
+    r2 = (x**2).sum(1)  # chi-square(3): the three components are jointly Gaussian, not just marginally
+    assert stats.kstest(r2, "chi2", args=(3,)).pvalue > 1e-4

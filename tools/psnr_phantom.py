@@ -46,6 +46,11 @@ CFGS = {
     # reference-default heads (sigma_net + slice variance: the learned variance is what weights the data term up against
     # the edge regulariser) on the 128^3 phantom, poses fixed: the reconstruction-quality run, --ours-only
     "3s": dict(sim=dict(n=128, n_stacks=3, res_r=1.0, res_s=1.0, gap=3.0), args=dict()),
+    # BASELINE config 3 at reduced size: stacks simulated at per-slice perturbed ("true") poses (rotation-vector offsets
+    # U(+-3 deg)^3, translations U(+-1.5 mm)^3), the NOMINAL stack poses handed to training, reference-default heads,
+    # joint pose + INR optimisation (models.py:275-278,357-363, train.py:224)
+    "3p": dict(sim=dict(n=64, n_stacks=6, res_r=1.0, res_s=1.0, gap=3.0, motion_deg=3.0, motion_mm=1.5),
+               args=dict(no_transformation_optimization=False)),
     # BASELINE config 2 in full (128^3, 16 levels, 64 x 3 hidden, B = 8192, S = 128, 5000 iterations): --ours-only
     "2": dict(sim=dict(n=128, n_stacks=3, res_r=1.0, res_s=1.0, gap=3.0),
               args=dict(n_levels=16, depth=3, width=64, no_pixel_variance=True, no_slice_variance=True)),
@@ -100,6 +105,71 @@ def phantom_grid(n, res_r):
     ax = (torch.arange(n, dtype=torch.float32) - (n - 1) / 2.0) * res_r
     zz, yy, xx = torch.meshgrid(ax, ax, ax, indexing="ij")
     return torch.stack((xx, yy, zz), -1).reshape(-1, 3)
+
+
+def _world_matrix(ax: torch.Tensor) -> torch.Tensor:
+    """[n,6] axis-angle (trans_first: x_world = R (x + T), transform.py:259-271) -> [n,4,4] slice-to-world matrices, fp64 on the CPU."""
+    from scipy.spatial.transform import Rotation
+
+    ax = ax.detach().double().cpu()
+    R = torch.from_numpy(Rotation.from_rotvec(ax[:, :3].numpy()).as_matrix())
+    M = torch.eye(4, dtype=torch.float64).repeat(ax.shape[0], 1, 1)
+    M[:, :3, :3] = R
+    M[:, :3, 3] = torch.einsum("nij,nj->ni", R, ax[:, 3:])
+    return M
+
+
+def pose_error(ax_est: torch.Tensor, ax_true: torch.Tensor) -> dict:
+    """Per-slice pose error up to the global rigid gauge (a reconstruction in a rigidly moved frame is as good):
+    G_i = M_est_i M_true_i^-1 maps the true world frame to the estimated one; the residual of G_i against the mean G is
+    reported as a rotation angle (degrees) and as the displacement of the slice centre (mm), mean and max over slices."""
+    Me, Mt = _world_matrix(ax_est), _world_matrix(ax_true)
+    G = Me @ torch.linalg.inv(Mt)
+    U, _, Vh = torch.linalg.svd(G[:, :3, :3].mean(0))
+    Rm = U @ torch.diag(torch.tensor([1.0, 1.0, float(torch.sign(torch.linalg.det(U @ Vh)))], dtype=torch.float64)) @ Vh
+    centre = Mt[:, :3, 3]  # true world position of every slice centre
+    moved = torch.einsum("nij,nj->ni", G[:, :3, :3], centre) + G[:, :3, 3]
+    tm = (moved - centre @ Rm.T).mean(0)
+    disp = (moved - (centre @ Rm.T + tm)).norm(dim=1)
+    Rres = Rm.T @ G[:, :3, :3]
+    ang = torch.rad2deg(torch.acos(((Rres.diagonal(dim1=1, dim2=2).sum(1) - 1) / 2).clamp(-1, 1)))
+    return {"rot_deg_mean": float(ang.mean()), "rot_deg_max": float(ang.max()), "centre_mm_mean": float(disp.mean()), "centre_mm_max": float(disp.max())}
+
+
+def run_pose_recovery(cfg_name="3p", n_iter=3000, batch=4096, n_samples=64, device=None, log=print):
+    """BASELINE config 3 as a WORKLOAD on the product path (nesvor_b200.train, fused kernel A with the pose gradient, transReg,
+    fused AdamW): pose error against the injected motion before (nominal stack poses) and after training, and the PSNR of the
+    reconstruction with and without pose optimisation on the same data."""
+    import nesvor_b200 as nb
+    from nesvor_b200.data.phantom import simulate_slices, stack_geometry
+    from nesvor_b200.nesvor.fused import attach_render_state, fused_render
+
+    device = device or torch.device("cuda", 0)
+    c = CFGS[cfg_name]
+    sim = c["sim"]
+    out = {"cfg": cfg_name, "iters": n_iter, "batch": batch, "n_samples": n_samples, "sim": sim}
+    _, n_slice = stack_geometry(sim["n"], sim["res_r"], sim["res_s"], sim["gap"])
+    grid = phantom_grid(sim["n"], sim["res_r"])
+    for tag, fixed in (("joint_pose_and_inr", False), ("poses_fixed_at_nominal", True)):
+        args = make_args(device, n_iter=n_iter, batch_size=batch, n_samples=n_samples, no_loss_sync=True,
+                         **dict(c["args"], no_transformation_optimization=fixed))
+        torch.manual_seed(0)
+        slices, volume, true_ax = simulate_slices(device=device, **sim)
+        keep = torch.tensor([s.stack_idx * n_slice + s.slice_idx for s in slices])
+        nominal = torch.cat([s.transformation.axisangle() for s in slices])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        inr, out_slices, _ = nb.train(slices, args)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        est = torch.cat([s.transformation.axisangle() for s in out_slices])
+        gt = volume[0, 0].reshape(-1).cpu()
+        attach_render_state(inr, args)
+        rec = torch.cat([fused_render(inr, grid[i : i + (1 << 18)].to(device), None, 0.0, 1).cpu() for i in range(0, grid.shape[0], 1 << 18)])
+        out[tag] = {"pose_error_before": pose_error(nominal, true_ax[keep]), "pose_error_after": pose_error(est, true_ax[keep]),
+                    "psnr_inside": psnr(rec, gt, gt > 0), "psnr_full": psnr(rec, gt), "train_wall_s": wall, "n_slices": len(slices)}
+        log(tag, json.dumps(out[tag]))
+    return out
 
 
 def run_ours_only(cfg_name="2", n_iter=5000, batch=8192, n_samples=128, device=None, log=print):
@@ -197,6 +267,12 @@ def run(cfg_name="1", n_iter=200, batch=2048, n_samples=32, device=None, threads
         "oracle_s_per_iter": t_cpu / n_iter, "ours_s_per_iter_incl_h2d_and_sync": t_gpu / n_iter,
         "host_threads": torch.get_num_threads(),
     }
+    if not args.no_transformation_optimization:  # joint pose + INR: the two optimisers must move the poses alike
+        ax_o = om.P["axisangle"].detach()
+        ax_n = model.axisangle.detach().cpu()
+        ax_0 = dataset.transformation.axisangle().detach().cpu()
+        out["pose_update_rel_l2_ours_vs_oracle"] = float(((ax_n - ax_0) - (ax_o - ax_0)).norm() / (ax_o - ax_0).norm().clamp_min(1e-30))
+        out["pose_update_norm_oracle"] = float((ax_o - ax_0).norm())
     out["abs_diff_inside_db"] = abs(out["psnr_ours_inside"] - out["psnr_oracle_inside"])
     out["abs_diff_full_db"] = abs(out["psnr_ours_full"] - out["psnr_oracle_full"])
     return out
@@ -209,12 +285,16 @@ def main():
     ap.add_argument("--batch", type=int, default=2048)
     ap.add_argument("--samples", type=int, default=32, help="PSF samples per pixel (the fused kernel needs 32..256)")
     ap.add_argument("--json", default=None)
+    ap.add_argument("--pose", action="store_true", help="config 3 as a workload: pose error before / after joint optimisation + PSNR (product path only)")
     ap.add_argument("--ours-only", action="store_true", help="train with nesvor_b200.train end to end (no oracle) and report PSNR + wall time")
     a = ap.parse_args()
     from nesvor_b200.csrc import build as nsv_build
 
     nsv_build.build()
-    out = run_ours_only(a.cfg, a.iters, a.batch, a.samples) if a.ours_only else run(a.cfg, a.iters, a.batch, a.samples)
+    if a.pose:
+        out = run_pose_recovery(a.cfg, a.iters, a.batch, a.samples)
+    else:
+        out = run_ours_only(a.cfg, a.iters, a.batch, a.samples) if a.ours_only else run(a.cfg, a.iters, a.batch, a.samples)
     print(json.dumps(out))
     if a.json:
         with open(a.json, "w") as f:
