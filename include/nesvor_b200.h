@@ -280,6 +280,19 @@ int nsv_adamw_step_dp(float* param, const void* const* peer_grads, float* exp_av
                       void* const* peer_param_f16, int world, int rank, int64_t n, float lr, float beta1, float beta2,
                       float eps, float weight_decay, int step, float grad_unscale,
                       int64_t f32_lo /* multiple of 4 */, void* const* peer_param_f32 /* or NULL */, void* stream);
+/* The same kernel with the rendezvous of the ranks INSIDE it (no host-launched barrier around it): `peer_flags[r]` = rank r's
+ * flag block (64 x uint64 in peer-accessible memory, zero-initialised once and made visible to all ranks before the first
+ * call), `epoch` = a positive number that is the same on every rank for a given step and strictly increases from step to
+ * step.  Prologue: every rank announces "my gradient is complete" (it is: the producing kernel precedes this launch on
+ * `stream`) to every rank and waits for all announcements before pulling gradients; epilogue: the rank's last block announces
+ * "all my reads and my writes into your copies are done" and waits for the same from every rank, so that when the kernel
+ * completes the local fp16 / fp32 copies are whole and the local gradient may be cleared.  A wait gives up after a few
+ * seconds (a dead rank must not hang the others' GPUs) and records the epoch in flag word 33. */
+int nsv_adamw_step_dp_sync(float* param, const void* const* peer_grads, float* exp_avg, float* exp_avg_sq,
+                           void* const* peer_param_f16, int world, int rank, int64_t n, float lr, float beta1, float beta2,
+                           float eps, float weight_decay, int step, float grad_unscale, int64_t f32_lo,
+                           void* const* peer_param_f32, void* const* peer_flags, uint64_t epoch, void* stream);
+
 
 /* tcgen05 / TMEM bring-up check used by tests/test_gpu_umma.py: runs every tensor-core operand
  * configuration kernel A uses on fixed 128x64 / 64x64 / 128x16 fp16 inputs (no reference counterpart). */

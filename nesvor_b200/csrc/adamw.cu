@@ -69,15 +69,51 @@ struct PeerPtrs {
   const float* grad[kMaxPeers];
   __half* p16[kMaxPeers];
   float* p32[kMaxPeers];  // optional fp32 mirror of the elements [f32_lo, n): the per-slice parameters kernel A reads in fp32
+  // optional in-kernel rendezvous (replaces the two host-launched symmetric-memory barriers around the kernel):
+  // flags[r] = rank r's flag block in peer memory, 64 x u64: [0,16) "gradient of rank i complete" (written by rank i),
+  // [16,32) "rank i has read every gradient and written every fp16 / fp32 copy", [32] block ticket counter, [33] time-out marker
+  unsigned long long* flags[kMaxPeers];
 };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// spins on a flag in THIS rank's memory until it reaches `want`; gives up after ~4 s of cycles (a rank that died must not
+// hang the others' GPUs) and leaves a marker the host checks
+__device__ __forceinline__ void wait_flag(unsigned long long* flags_mine, int slot, unsigned long long want) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flags_mine + slot) < want) {
+    if (clock64() - t0 > (8ll << 30)) {
+      flags_mine[33] = want;
+      break;
+    }
+    __nanosleep(64);
+  }
+}
 
 // WORLD > 0: compile-time rank count (all peer loads of an element group are in flight together); 0: run-time loop
 template <int WORLD>
 __global__ void __launch_bounds__(256) adamw_dp_kernel(float* __restrict__ p, const __grid_constant__ PeerPtrs peers, float* __restrict__ m,
                                                        float* __restrict__ v, int world_rt, int64_t lo, int64_t hi, int64_t f32_lo, float lr,
                                                        float b1, float b2, float eps, float wd, float step_size, float inv_sqrt_bc2,
-                                                       float unscale) {
+                                                       float unscale, int rank, unsigned long long epoch) {
   const int world = WORLD > 0 ? WORLD : world_rt;
+  const bool rendezvous = peers.flags[0] != nullptr;
+  if (rendezvous) {
+    // (1) this rank's gradient is complete (kernel A precedes this launch on the stream): tell every rank; then every block
+    // waits until every rank has said so before it pulls gradients through the peer pointers
+    if (threadIdx.x == 0) {
+      if (blockIdx.x == 0)
+        for (int r = 0; r < world; ++r) st_release_sys(peers.flags[r] + rank, epoch);
+      for (int r = 0; r < world; ++r) wait_flag(peers.flags[rank], r, epoch);
+    }
+    __syncthreads();
+  }
   // lo is a multiple of 4 (16-byte aligned vectors); the ragged tail of the last shard is handled element-wise
   const int64_t n4 = (hi - lo) >> 2;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
@@ -137,6 +173,23 @@ __global__ void __launch_bounds__(256) adamw_dp_kernel(float* __restrict__ p, co
     if (e >= f32_lo)
       for (int r = 0; r < world; ++r) peers.p32[r][e - f32_lo] = pi;
   }
+  if (rendezvous) {
+    // (2) the last block of this rank to finish announces "all my reads and all my writes into your copies are done" and
+    // then waits for the same announcement of every rank: when the kernel ends, this rank's fp16 / fp32 copies are complete
+    // (the next kernel A may read them) and nobody reads this rank's gradient any more (it may be cleared)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      unsigned long long* mine = peers.flags[rank];
+      const unsigned long long ticket = atomicAdd(mine + 32, 1ull);
+      if (ticket == (unsigned long long)gridDim.x - 1ull) {
+        __threadfence_system();
+        mine[32] = 0ull;
+        for (int r = 0; r < world; ++r) st_release_sys(peers.flags[r] + 16 + rank, epoch);
+        for (int r = 0; r < world; ++r) wait_flag(mine, 16 + r, epoch);
+      }
+    }
+  }
 }
 
 }  // namespace
@@ -151,10 +204,10 @@ extern "C" int nsv_adamw_shard_bounds(int64_t n, int world, int rank, int64_t* l
   return NSV_OK;
 }
 
-extern "C" int nsv_adamw_step_dp(float* param, const void* const* peer_grads, float* exp_avg, float* exp_avg_sq,
-                                 void* const* peer_param_f16, int world, int rank, int64_t n, float lr, float beta1, float beta2,
-                                 float eps, float weight_decay, int step, float grad_unscale, int64_t f32_lo,
-                                 void* const* peer_param_f32, void* stream) {
+static int adamw_step_dp_impl(float* param, const void* const* peer_grads, float* exp_avg, float* exp_avg_sq,
+                             void* const* peer_param_f16, int world, int rank, int64_t n, float lr, float beta1, float beta2,
+                             float eps, float weight_decay, int step, float grad_unscale, int64_t f32_lo,
+                             void* const* peer_param_f32, void* const* peer_flags, uint64_t epoch, void* stream) {
   using namespace nsv;
   NSV_REQUIRE(n >= 0 && step >= 1, "nsv_adamw_step_dp: bad n / step");
   NSV_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "nsv_adamw_step_dp: world must be 1..16, rank in [0, world)");
@@ -166,25 +219,45 @@ extern "C" int nsv_adamw_step_dp(float* param, const void* const* peer_grads, fl
     pp.grad[r] = r < world ? (const float*)peer_grads[r] : nullptr;
     pp.p16[r] = r < world ? (__half*)peer_param_f16[r] : nullptr;
     pp.p32[r] = (r < world && peer_param_f32) ? (float*)peer_param_f32[r] : nullptr;
+    pp.flags[r] = (r < world && peer_flags) ? (unsigned long long*)peer_flags[r] : nullptr;
+    NSV_REQUIRE(r >= world || !peer_flags || pp.flags[r], "nsv_adamw_step_dp_sync: NULL flag pointer");
     NSV_REQUIRE(r >= world || (pp.grad[r] && pp.p16[r]), "nsv_adamw_step_dp: NULL peer pointer");
     NSV_REQUIRE(r >= world || f32_lo >= n || (pp.p32[r] && (uintptr_t)pp.p32[r] % 16 == 0), "nsv_adamw_step_dp: NULL / unaligned fp32 mirror pointer");
   }
   int64_t lo = 0, hi = 0;
   nsv_adamw_shard_bounds(n, world, rank, &lo, &hi);
-  if (hi <= lo) return NSV_OK;
+  if (hi <= lo && !peer_flags) return NSV_OK;  // with the in-kernel rendezvous an empty shard still takes part in it
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   const float step_size = (float)((double)lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
   const int64_t blocks = ((hi - lo) / 4 + 255) / 256 + 1;
   const int grid = (int)(blocks < (int64_t)num_sms() * 8 ? blocks : (int64_t)num_sms() * 8);
 #define NSV_DP_LAUNCH(W)                                                                                                            \
   adamw_dp_kernel<W><<<grid, 256, 0, (cudaStream_t)stream>>>(param, pp, exp_avg, exp_avg_sq, world, lo, hi, f32_lo, lr, beta1, beta2, eps, weight_decay, \
-                                                             step_size, inv_sqrt_bc2, grad_unscale)
+                                                             step_size, inv_sqrt_bc2, grad_unscale, rank, (unsigned long long)epoch)
   if (world == 2) NSV_DP_LAUNCH(2);
   else if (world == 4) NSV_DP_LAUNCH(4);
   else if (world == 8) NSV_DP_LAUNCH(8);
   else NSV_DP_LAUNCH(0);
 #undef NSV_DP_LAUNCH
   return check_launch("nsv_adamw_step_dp");
+}
+
+extern "C" int nsv_adamw_step_dp(float* param, const void* const* peer_grads, float* exp_avg, float* exp_avg_sq,
+                                 void* const* peer_param_f16, int world, int rank, int64_t n, float lr, float beta1, float beta2,
+                                 float eps, float weight_decay, int step, float grad_unscale, int64_t f32_lo,
+                                 void* const* peer_param_f32, void* stream) {
+  return adamw_step_dp_impl(param, peer_grads, exp_avg, exp_avg_sq, peer_param_f16, world, rank, n, lr, beta1, beta2, eps, weight_decay,
+                            step, grad_unscale, f32_lo, peer_param_f32, nullptr, 0, stream);
+}
+
+extern "C" int nsv_adamw_step_dp_sync(float* param, const void* const* peer_grads, float* exp_avg, float* exp_avg_sq,
+                                      void* const* peer_param_f16, int world, int rank, int64_t n, float lr, float beta1, float beta2,
+                                      float eps, float weight_decay, int step, float grad_unscale, int64_t f32_lo,
+                                      void* const* peer_param_f32, void* const* peer_flags, uint64_t epoch, void* stream) {
+  using namespace nsv;
+  NSV_REQUIRE(peer_flags && epoch > 0, "nsv_adamw_step_dp_sync: needs the ranks' flag blocks and a positive, strictly increasing epoch");
+  return adamw_step_dp_impl(param, peer_grads, exp_avg, exp_avg_sq, peer_param_f16, world, rank, n, lr, beta1, beta2, eps, weight_decay,
+                            step, grad_unscale, f32_lo, peer_param_f32, peer_flags, epoch, stream);
 }
 
 extern "C" int nsv_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* param_f16, int64_t n, float lr,

@@ -155,7 +155,8 @@ class FusedState:
         n_grad_pad = (n_grad + 255) // 256 * 256
         n_f16_pad = (self.flat16.numel() * 2 + 255) // 256 * 256
         n_tail = self.n_total - self.tail_lo
-        nbytes = n_grad_pad + n_f16_pad + n_tail * 4
+        n_tail_pad = (n_tail * 4 + 255) // 256 * 256
+        nbytes = n_grad_pad + n_f16_pad + n_tail_pad + 512  # + 64 x u64 rendezvous flags (nsv_adamw_step_dp_sync)
         buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
         handle = symm_mem.rendezvous(buf, group)
         grad = buf[:n_grad].view(torch.float32)
@@ -164,7 +165,7 @@ class FusedState:
         flat16.copy_(self.flat16)
         self.grad, self.flat16 = grad, flat16
         if n_tail > 0:  # only the owner of a shard updates its fp32 master: the owner mirrors the per-slice parameters everywhere
-            tail32 = buf[n_grad_pad + n_f16_pad : nbytes].view(torch.float32)
+            tail32 = buf[n_grad_pad + n_f16_pad : n_grad_pad + n_f16_pad + n_tail * 4].view(torch.float32)
             tail32.copy_(self.flat[self.tail_lo :])
             self.tail32 = tail32
         self.losses = self.grad[self.n_total : self.n_total + 8]
@@ -174,6 +175,10 @@ class FusedState:
         self.peer_grads = (ctypes.c_void_p * world)(*ptrs)
         self.peer_flat16 = (ctypes.c_void_p * world)(*[p + n_grad_pad for p in ptrs])
         self.peer_tail32 = (ctypes.c_void_p * world)(*[p + n_grad_pad + n_f16_pad for p in ptrs]) if n_tail > 0 else None
+        self.dp_flags = buf[n_grad_pad + n_f16_pad + n_tail_pad :].view(torch.int64)
+        self.dp_flags.zero_()
+        self.peer_flags = (ctypes.c_void_p * world)(*[p + n_grad_pad + n_f16_pad + n_tail_pad for p in ptrs])
+        torch.cuda.synchronize(self.device)
         handle.barrier()  # every rank's copy is initialised before anyone's optimiser writes into it
 
     def disable_peer_memory(self) -> None:
@@ -181,7 +186,7 @@ class FusedState:
         self.grad, self.flat16 = self.grad.clone(), self.flat16.clone()
         self.losses = self.grad[self.n_total : self.n_total + 8]
         self.tail32 = None
-        self._symm_buf = self.peer_handle = self.peer_grads = self.peer_flat16 = self.peer_tail32 = None
+        self._symm_buf = self.peer_handle = self.peer_grads = self.peer_flat16 = self.peer_tail32 = self.peer_flags = self.dp_flags = None
 
     # ------------------------------------------------------------------ model <-> flat
     def seg(self, name: str, buf: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
@@ -448,6 +453,18 @@ class FusedTrainer:
         rank = dist.get_rank()
         if self.dp_mode is None:
             self._setup_dp(dist, world)
+        if self.dp_mode == "peer" and getattr(self.args, "dp_sync", "kernel") == "kernel":
+            # ONE launch: rendezvous of the ranks (flags in peer memory), reduce-scatter, AdamW, all-gather, rendezvous
+            with torch.cuda.device(st.device):
+                rc = _lib.lib().nsv_adamw_step_dp_sync(
+                    _lib.ptr(st.flat), st.peer_grads, _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), st.peer_flat16,
+                    ctypes.c_int(world), ctypes.c_int(rank), ctypes.c_int64(st.n_train), ctypes.c_float(self.lr), ctypes.c_float(0.9),
+                    ctypes.c_float(0.99), ctypes.c_float(1e-15), ctypes.c_float(1e-2), ctypes.c_int(self.iteration),
+                    ctypes.c_float(1.0 / world), ctypes.c_int64(st.tail_lo), st.peer_tail32, st.peer_flags,
+                    ctypes.c_uint64(self.iteration), _lib.stream(st.device))
+            _lib.check(rc, "nsv_adamw_step_dp_sync")
+            st.grad[: st.n_train].zero_()
+            return
         if self.dp_mode == "peer":
             h = st.peer_handle
             h.barrier()  # every rank's kernel A has finished: all gradients are complete
@@ -472,6 +489,8 @@ class FusedTrainer:
         _lib.check(rc, "nsv_adamw_step")
 
     def sync_to_model(self) -> None:
+        if self.dp_mode == "peer" and getattr(self.state, "dp_flags", None) is not None and int(self.state.dp_flags[33]) != 0:
+            raise RuntimeError(f"data-parallel optimiser: a rendezvous timed out at step {int(self.state.dp_flags[33])} (a rank stopped responding)")
         if self.dp_mode == "peer":  # every rank holds only its own shard of the fp32 master: collect the others
             import torch.distributed as dist
 

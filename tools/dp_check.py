@@ -36,15 +36,18 @@ def main():
     slices, _, _ = simulate_slices(device=dev, n=48, n_stacks=3, res_r=1.0, res_s=1.0, gap=2.0, motion_deg=2.0, motion_mm=1.0)
     dataset = Dataset(slices, args)
     trainers = {}
-    for mode in ("peer", "allreduce"):
-        torch.manual_seed(7)  # identical initial parameters on every rank and for both trainers
+    # "peer": the fused kernel with the ranks' rendezvous inside it (nsv_adamw_step_dp_sync, the default);
+    # "peer_host": the same kernel bracketed by two host-launched symmetric-memory barriers (nsv_adamw_step_dp)
+    for mode in ("peer", "peer_host", "allreduce"):
+        torch.manual_seed(7)  # identical initial parameters on every rank and for all trainers
         model = nb.NeSVoR(dataset.transformation, dataset.resolution, dataset.mean, dataset.bounding_box, args)
         a = copy.copy(args)
-        a.dp_optimizer = mode
+        a.dp_optimizer = "peer" if mode == "peer_host" else mode
+        a.dp_sync = "host" if mode == "peer_host" else "kernel"
         trainers[mode] = FusedTrainer(model, a)
     g = torch.Generator().manual_seed(100 + rank)
     P = dataset.xyz.shape[0]
-    tp, ta = trainers["peer"], trainers["allreduce"]
+    tp, th, ta = trainers["peer"], trainers["peer_host"], trainers["allreduce"]
     for name in ("slice_embedding", "logit_coef", "log_var_slice", "axisangle"):
         t = tp.state.seg(name)
         if t is not None:
@@ -55,19 +58,23 @@ def main():
         batch = dict(xyz=dataset.xyz[sel], v=dataset.v[sel], slice_idx=dataset.slice_idx[sel])
         # kernel A accumulates with float atomics (run-to-run round-off that Adam's normalisation amplifies), so the two
         # optimiser paths are compared on the SAME per-rank gradient: one forward / backward, copied into both trainers
-        for tr in (tp, ta):
+        for tr in (tp, th, ta):
             tr.iteration += 1
             tr.state.losses.zero_()
         ta.state.forward_backward(batch["xyz"], batch["v"], batch["slice_idx"], noise)
         if it == 0:
             tp._setup_dp(dist, world)
+            th._setup_dp(dist, world)
         tp.state.grad[: tp.state.n_total].copy_(ta.state.grad[: ta.state.n_total])
-        for tr in (tp, ta):
+        th.state.grad[: th.state.n_total].copy_(ta.state.grad[: ta.state.n_total])
+        for tr in (tp, th, ta):
             tr._dp_update(dist, world)
         # the next forward must see the same parameters in both trainers (checked at the end); keep them in lockstep
     torch.cuda.synchronize()
     assert tp.dp_mode == "peer" and ta.dp_mode == "allreduce", (tp.dp_mode, ta.dp_mode)
     n = tp.state.n_train
+    assert th.dp_mode == "peer"
+    d_host = (th.state.flat16[:n].float() - tp.state.flat16[:n].float()).abs().max().item()  # the two synchronisation schemes: same kernel, same bits
     d16 = (tp.state.flat16[:n].float() - ta.state.flat16[:n].float()).abs().max().item()
     changed = (tp.state.flat16[:n] != 0).float().mean().item()
     # the per-slice parameters kernel A reads in fp32 (slice embedding, slice scale / variance, poses) must be current on
@@ -86,10 +93,10 @@ def main():
     ref = tp.state.flat16[:n].clone()
     dist.broadcast(ref, src=0)
     same = bool((ref == tp.state.flat16[:n]).all())
-    out = dict(rank=rank, world=world, max_abs_diff_fp16=d16, max_abs_diff_fp32_master=d32, max_abs_diff_per_slice_fp32=d_tail,
+    out = dict(rank=rank, world=world, max_abs_diff_kernel_vs_host_sync=d_host, rendezvous_timeouts=int(tp.state.dp_flags[33]), max_abs_diff_fp16=d16, max_abs_diff_fp32_master=d32, max_abs_diff_per_slice_fp32=d_tail,
                param_scale=scale, replicas_identical=same, nonzero_frac=changed)
     print(json.dumps(out), flush=True)
-    ok = same and d16 <= (0.0 if world == 2 else 2e-3 * scale) and d32 <= (0.0 if world == 2 else 1e-4 * scale)
+    ok = same and d_host == 0.0 and int(tp.state.dp_flags[33]) == 0 and d16 <= (0.0 if world == 2 else 2e-3 * scale) and d32 <= (0.0 if world == 2 else 1e-4 * scale)
     ok = ok and d_tail <= (0.0 if world == 2 else 1e-4 * scale)
     dist.barrier()
     dist.destroy_process_group()
