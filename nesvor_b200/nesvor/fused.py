@@ -453,7 +453,11 @@ class FusedTrainer:
         rank = dist.get_rank()
         if self.dp_mode is None:
             self._setup_dp(dist, world)
-        if self.dp_mode == "peer" and getattr(self.args, "dp_sync", "kernel") == "kernel":
+        if self.dp_mode == "peer" and getattr(self.args, "dp_sync", None) is None:
+            import os
+
+            self.args.dp_sync = os.environ.get("NSV_DP_SYNC", "kernel")  # "kernel" (rendezvous inside the kernel) | "host" (two barriers)
+        if self.dp_mode == "peer" and self.args.dp_sync == "kernel":
             # ONE launch: rendezvous of the ranks (flags in peer memory), reduce-scatter, AdamW, all-gather, rendezvous
             with torch.cuda.device(st.device):
                 rc = _lib.lib().nsv_adamw_step_dp_sync(
