@@ -226,6 +226,10 @@ int nsv_set_fused_impl(int impl);
  * (idx_lo, idx_hi, 0, 0) and key (seed_lo, seed_hi) -> Box-Muller.  normals [n,3] f32 and / or raw [n,4] u32 (either may be
  * NULL). */
 int nsv_debug_normal3(uint64_t seed, uint64_t offset, int64_t n, float* normals, uint32_t* raw, void* stream);
+/* Tile order of the tcgen05 training kernel: 0 (default; env NSV_TILE_ORDER) tiles strided over the CTAs, 1 one contiguous
+ * run of tiles per CTA -- with a spatially ordered batch (Dataset locality_batch_size) a CTA then walks neighbouring pixels
+ * of one slice; -1 back to the default.  Results are identical either way (the losses are means over the batch). */
+int nsv_set_fused_tile_order(int contiguous);
 /* Number of leading dense levels of the fp16 table that the tcgen05 training kernel stages into shared memory with one
  * bulk copy per CTA (TMA engine, cp.async.bulk) and gathers from there: -1 as many as fit beside the operand tiles
  * (default; env NSV_SMEM_LEVELS), 0 none, -2 back to the default.  Profiling / test hook. */

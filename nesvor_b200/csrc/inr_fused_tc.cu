@@ -262,7 +262,13 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
     if (wide) cta_barrier_all(); else group_barrier(grp, kGT);
   };
 
-  for (int64_t tile = (int64_t)blockIdx.x * kNGroups + grp; tile < n_tiles; tile += (int64_t)gridDim.x * kNGroups) {
+  // tile order: strided over the grid, or one contiguous run of tiles per CTA (an even count, so that the two halves of a
+  // 256-sample pixel stay in one CTA) -- with a spatially ordered batch the CTA then walks neighbouring pixels
+  const int64_t run = ((n_tiles / kNGroups + gridDim.x - 1) / gridDim.x) * kNGroups;
+  const int64_t tile_first = a.tile_order ? blockIdx.x * run + grp : (int64_t)blockIdx.x * kNGroups + grp;
+  const int64_t tile_stop = a.tile_order ? (n_tiles < (blockIdx.x + 1) * run ? n_tiles : (blockIdx.x + 1) * run) : n_tiles;
+  const int64_t tile_step = a.tile_order ? kNGroups : (int64_t)gridDim.x * kNGroups;
+  for (int64_t tile = tile_first; tile < tile_stop; tile += tile_step) {
     // ================= phase 0: sample geometry + encoding (lane pair = sample) =================
     tick(1);
     const int64_t sidx = tile * kGR + srow;

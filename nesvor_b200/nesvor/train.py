@@ -46,6 +46,12 @@ class Dataset(object):
         self.count = self.v.shape[0]
         self.epoch = 0
         self.dist = None  # set by train() under data parallelism: the epoch permutation is then broadcast from rank 0
+        # locality-aware batch order (SURVEY s.8f row 1): after the epoch shuffle the pixels of EVERY batch are put in
+        # (slice, row, column) order -- the batches keep the reference's composition (train.py:60-75: consecutive blocks of
+        # one randperm; every loss is a mean over the batch, so the order inside a batch is immaterial to the optimisation),
+        # but consecutive tiles of kernel A now belong to neighbouring pixels of one slice and share coarse / mid-level
+        # table entries in L1 / L2.  One sort per epoch (P keys), nothing per iteration.
+        self.locality_batch = int(getattr(args, "locality_batch_size", 0) or 0)
 
     @property
     def xyz_transformed(self) -> torch.Tensor:
@@ -70,10 +76,25 @@ class Dataset(object):
             idx = torch.randperm(self.xyz.shape[0], device=device)
             if self.dist is not None:
                 self.dist.broadcast(idx, src=0)
+            if self.locality_batch:
+                idx = self._order_inside_batches(idx, self.locality_batch)
             self.xyz, self.v, self.slice_idx = self.xyz[idx], self.v[idx], self.slice_idx[idx]
         sl = slice(self.count, self.count + batch_size)
         self.count += batch_size
         return {"xyz": self.xyz[sl], "v": self.v[sl], "slice_idx": self.slice_idx[sl]}
+
+    def _order_inside_batches(self, idx: torch.Tensor, batch_size: int) -> torch.Tensor:
+        """`idx` = the epoch's permutation of the pixel table; returns it with every consecutive block of `batch_size`
+        entries sorted by (slice, y, x) of the pixels they select.  Keys are built so that ONE stable sort does it."""
+        n = idx.numel()
+        xyz = self.xyz[idx]
+        lo = self.xyz.amin(0)
+        step = float(self.resolution[:, :2].min())
+        ix = ((xyz[:, 0] - lo[0]) / step).round().long().clamp_(0, (1 << 13) - 1)
+        iy = ((xyz[:, 1] - lo[1]) / step).round().long().clamp_(0, (1 << 13) - 1)
+        block = torch.arange(n, device=idx.device) // batch_size
+        key = ((block << 20 | self.slice_idx[idx].long()) << 26) | (iy << 13) | ix
+        return idx[torch.argsort(key)]
 
     @property
     def mask(self) -> Volume:

@@ -94,3 +94,38 @@ def test_unsupported_configurations_raise(native_lib):
                dict(n_features_z=7), dict(depth=2)):
         with pytest.raises(FusedUnsupported):
             FusedState(model.inr, make_args(**kw), model)
+
+
+def test_locality_aware_batch_order_keeps_the_batches():
+    """Dataset(locality_batch_size=B) (SURVEY s.8f row 1; reference batching: nesvor/nesvor/train.py:60-75): after the epoch
+    shuffle every consecutive block of B pixels is put in (slice, y, x) order -- same batch membership as the reference's
+    randperm blocks, spatially ordered inside."""
+    from argparse import Namespace
+
+    import torch
+
+    from nesvor_b200.nesvor.train import Dataset
+    from nesvor_b200.transform import RigidTransform
+
+    class FakeSlice:
+        def __init__(self, i, n=500):
+            g = torch.Generator().manual_seed(i)
+            self.xyz_masked_untransformed = torch.cat([torch.randint(0, 60, (n, 2), generator=g).float() - 30, torch.zeros(n, 1)], 1)
+            self.v_masked = torch.rand(n, generator=g)
+            self.transformation = RigidTransform(torch.eye(3, 4)[None])
+            self.resolution_xyz = torch.tensor([1.0, 1.0, 3.0])
+
+    ds = Dataset([FakeSlice(i) for i in range(6)], Namespace(locality_batch_size=256))
+    idx = torch.randperm(3000, generator=torch.Generator().manual_seed(0))
+    out = ds._order_inside_batches(idx, 256)
+    for b in range(0, 3000, 256):
+        assert sorted(idx[b : b + 256].tolist()) == sorted(out[b : b + 256].tolist())
+        sl = ds.slice_idx[out[b : b + 256]]
+        assert (sl[1:] >= sl[:-1]).all()
+        same = sl[1:] == sl[:-1]
+        y = ds.xyz[out[b : b + 256], 1]
+        assert (y[1:][same] >= y[:-1][same]).all()
+    # and through get_batch: an epoch of batches covers every pixel exactly once
+    ds.count = ds.xyz.shape[0]
+    seen = torch.cat([ds.get_batch(256, torch.device("cpu"))["v"] for _ in range(3000 // 256)])
+    assert seen.numel() == 2816 and torch.unique(seen).numel() == seen.numel()

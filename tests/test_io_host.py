@@ -152,3 +152,35 @@ def test_inputs_outputs_mirror_cli_io(tmp_path):
 
     back = load_volume(out_args.output_volume)
     assert torch.allclose(back.image, vol.image * vol.mask, rtol=1e-6)
+
+
+def test_reads_a_checkpoint_written_by_the_reference_writer(tmp_path):
+    """tests/golden/reference_model.pt was written by the reference's OWN `cli/io.py::outputs` with the reference's own INR /
+    Volume / RigidTransform classes (tests/golden/make_golden_model_pt.py, on nesvor_b200.compat): `load_model` must rebuild
+    the INR from the file's args and return the stored tensors, mask and pose; when a copy of the reference is at hand the
+    file is regenerated in a subprocess and must carry the same tensors (the fixture is not stale)."""
+    import os
+    import subprocess
+
+    import numpy as np
+
+    from nesvor_b200.io import load_model
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    want = np.load(os.path.join(gold, "reference_model_tensors.npz"))
+
+    def check(path):
+        inr, mask, args = load_model(path, torch.device("cpu"))
+        sd = inr.state_dict()
+        for k in ("bounding_box", "encoding.params", "density_net.params"):
+            assert np.array_equal(sd[k].float().numpy(), want[k]), k
+        assert np.array_equal(mask.image.numpy(), want["mask_image"]) and np.array_equal(mask.mask.numpy(), want["mask_mask"])
+        assert np.allclose(mask.transformation.axisangle().numpy(), want["mask_axisangle"], atol=1e-6)
+        assert type(mask).__module__.startswith("nesvor_b200") and args.width == 64 and mask.resolution_x == 0.8
+
+    check(os.path.join(gold, "reference_model.pt"))
+    root = os.path.dirname(gold.rstrip(os.sep).rsplit(os.sep, 1)[0])
+    if any(os.path.isdir(os.path.join(p, "nesvor")) for p in ("/root/reference", os.path.join(root, "baseline", "_ref"))):
+        r = subprocess.run([sys.executable, os.path.join(gold, "make_golden_model_pt.py"), "--out", str(tmp_path)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-500:]
+        check(str(tmp_path / "reference_model.pt"))

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--cfg", type=int, default=2)
     ap.add_argument("--impl", default="auto")
     ap.add_argument("--ablate", default="0", help="comma list of NSV_ABLATE masks (1: no table loads, 2: no table reductions, 4: no MLP chain)")
+    ap.add_argument("--locality", default="0", help="comma list: 0 random order inside the batch + strided tiles, 1 (slice, y, x)-ordered batch + contiguous tiles per CTA")
     ap.add_argument("--timers", action="store_true", help="per-phase warp-cycle breakdown of the tcgen05 kernel (profiling build)")
     a = ap.parse_args()
     import torch
@@ -61,8 +62,14 @@ def main():
     batch = dataset.get_batch(B, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
-    for var in [(v, ab) for v in a.variants.split(",") for ab in a.ablate.split(",")]:
-        var, ablate = var
+    batch_random = batch
+    key = (batch["slice_idx"].long() << 26) | (((batch["xyz"][:, 1] - dataset.xyz[:, 1].min()).round().long().clamp(0, 8191)) << 13) | (batch["xyz"][:, 0] - dataset.xyz[:, 0].min()).round().long().clamp(0, 8191)
+    order = torch.argsort(key)
+    batch_sorted = {k: v[order].contiguous() for k, v in batch.items()}
+    for var in [(v, ab, loc) for v in a.variants.split(",") for ab in a.ablate.split(",") for loc in a.locality.split(",")]:
+        var, ablate, loc = var
+        batch = batch_sorted if int(loc) else batch_random
+        _lib.lib().nsv_set_fused_tile_order(int(loc))
         os.environ["NSV_ABLATE"] = ablate
         agg, fast, *rest = (int(x) for x in var.split(":"))
         smem = rest[0] if rest else -2  # third field: levels staged in shared memory (-1 as many as fit, 0 none)
@@ -79,10 +86,12 @@ def main():
             torch.cuda.synchronize()
             if i >= 3:
                 durs.append(k0.elapsed_time(k1))
-        print(json.dumps({"cfg": a.cfg, "impl": a.impl, "agg_max": agg, "fast": fast, "smem_levels": smem, "ablate": int(ablate), "ms_mean": sum(durs) / len(durs), "ms_min": min(durs),
+        print(json.dumps({"cfg": a.cfg, "impl": a.impl, "agg_max": agg, "fast": fast, "smem_levels": smem, "locality": int(loc), "ablate": int(ablate), "ms_mean": sum(durs) / len(durs), "ms_min": min(durs),
                           "gq_per_s": B * S / (min(durs) * 1e-3) / 1e9}), flush=True)
     _lib.set_fused_tuning(-1, -1)
     _lib.lib().nsv_set_fused_smem_levels(-2)
+    _lib.lib().nsv_set_fused_tile_order(-1)
+    batch = batch_random
     if args.n_levels_bias:  # the mean(log_bias) pre-pass alone (part of every forward_backward timed above)
         import ctypes
 

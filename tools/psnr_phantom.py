@@ -273,6 +273,7 @@ def run(cfg_name="1", n_iter=200, batch=2048, n_samples=32, device=None, threads
         ax_0 = dataset.transformation.axisangle().detach().cpu()
         out["pose_update_rel_l2_ours_vs_oracle"] = float(((ax_n - ax_0) - (ax_o - ax_0)).norm() / (ax_o - ax_0).norm().clamp_min(1e-30))
         out["pose_update_norm_oracle"] = float((ax_o - ax_0).norm())
+        out["pose_update_cosine_ours_vs_oracle"] = float(torch.nn.functional.cosine_similarity((ax_n - ax_0).flatten(), (ax_o - ax_0).flatten(), dim=0))
     out["abs_diff_inside_db"] = abs(out["psnr_ours_inside"] - out["psnr_oracle_inside"])
     out["abs_diff_full_db"] = abs(out["psnr_ours_full"] - out["psnr_oracle_full"])
     return out
