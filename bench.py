@@ -207,6 +207,40 @@ def kernel_b_leg(dev, flush, reps=5):
             "ms": ms, "pixels_per_s": n_px / (ms * 1e-3), "algorithmic_bytes": alg, "achieved": alg / (ms * 1e-3) / 1e9, "unit": "GB/s"}
 
 
+def render_leg(dev, model, args, flush, reps=5):
+    """Inference side of the path (sample.py:17-53, `sample_points` / `sample_slice`): the forward-only fused kernel
+    nsv_inr_render on one inference batch of `nesvor reconstruct` for this configuration -- 8 x batch_size points x
+    2 x n_samples PSF samples (cli/commands.py:94-97) = 16.8 M queries per launch.  Algorithmic bytes per query
+    (SURVEY s.8d): L x 8 x F x 2 B = 512 B of fp16 table gathers."""
+    import torch
+    from nesvor_b200.nesvor.fused import attach_render_state, fused_render
+
+    try:
+        M, S = 8 * args.batch_size, 2 * args.n_samples
+        st = attach_render_state(model.inr, args)
+        bb = model.inr.bounding_box
+        g = torch.Generator(device=dev).manual_seed(3)
+        xyz = bb[0] + (bb[1] - bb[0]) * (0.1 + 0.8 * torch.rand(M, 3, device=dev, generator=g))
+        durs = []
+        for i in range(2 + reps):
+            flush.zero_()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            out = fused_render(model.inr, xyz, None, 0.4247, S, state=st)
+            k1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                durs.append(k0.elapsed_time(k1))
+        ms = sorted(durs)[len(durs) // 2]
+        L = st.cfg.grid.n_levels
+        alg = M * S * L * 8 * 2 * 2
+        return {"op": "nsv_inr_render (forward only: sample generation, hash-grid gather, MLP, softplus, PSF mean)", "points": M, "n_samples": S,
+                "queries": M * S, "ms": ms, "queries_per_s": M * S / (ms * 1e-3), "algorithmic_bytes": alg, "achieved": alg / (ms * 1e-3) / 1e9,
+                "unit": "GB/s", "finite": bool(torch.isfinite(out).all())}
+    except Exception as e:  # informative leg
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def other_heads_leg(dev, steps=50):
     """Whole fused iteration (kernel A [+ the mean(log_bias) pre-pass] + finalize + transReg + AdamW, device-resident batches)
     at 2^20 queries for the head configurations of BASELINE configs 3 and 5 -- informative only; the bench line's
@@ -442,6 +476,7 @@ def run_ours(a):
             durs.append(k0.elapsed_time(k1))
     k_ms = sum(durs) / len(durs)
     kernel_b = kernel_b_leg(dev, flush)
+    render = render_leg(dev, model, args, flush) if world == 1 else None
     other_heads = other_heads_leg(dev) if world == 1 else None
     if world == 1:  # kernel B next to the reference's own CUDA extension on this GPU (subprocess: foreign kernels stay out of this context)
         try:
@@ -484,6 +519,8 @@ def run_ours(a):
             "clocks": clocks.summary(), "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": 3 * a.steps, "roofline": roofline, "kernel_b": dict(kernel_b, frac=kernel_b["achieved"] / peak, peak=peak),
             "losses_last_step": {k: float(v) for k, v in losses.items()}}
+    if render is not None:
+        line["render"] = dict(render, frac=render["achieved"] / peak) if "achieved" in render else render
     if cpu is not None:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "full_batch_iteration")}
     if other_heads is not None:

@@ -15,6 +15,10 @@ namespace {
 __device__ __forceinline__ void adamw_update(float g, float& pi, float& mi, float& vi, float lr, float b1, float b2, float eps, float wd,
                                              float step_size, float inv_sqrt_bc2, float unscale) {
   g *= unscale;
+  // found-inf guard, element-wise: the reference's GradScaler skips an optimiser step whose gradient holds an inf / NaN
+  // (train.py:161-164,195); here an element whose gradient is not finite keeps its parameter and both moments (the fp16
+  // backward operands overflow before fp32 does, and one poisoned element must not poison Adam's state for good)
+  if (!(fabsf(g) <= 3.0e38f)) return;
   pi *= 1.f - lr * wd;
   mi = b1 * mi + (1.f - b1) * g;
   vi = b2 * vi + (1.f - b2) * g * g;
@@ -119,6 +123,7 @@ __global__ void __launch_bounds__(256) adamw_dp_kernel(float* __restrict__ p, co
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
   auto update = [&](float g, float& pi, float& mi, float& vi) {
     g *= unscale;
+    if (!(fabsf(g) <= 3.0e38f)) return;  // found-inf guard (see adamw_update): identical on every owner, the sum is the same everywhere
     pi *= 1.f - lr * wd;
     mi = b1 * mi + (1.f - b1) * g;
     vi = b2 * vi + (1.f - b2) * g * g;

@@ -16,6 +16,7 @@ def main():
     ap.add_argument("--fixed", type=int, default=1)
     ap.add_argument("--iters", type=int, default=3000)
     ap.add_argument("--impl", default="auto")
+    ap.add_argument("--mode", default="step", choices=["step", "train"], help="train: through nesvor_b200.train + the evaluation of psnr_phantom.run_pose_recovery")
     a = ap.parse_args()
     import torch
 
@@ -32,6 +33,28 @@ def main():
     args = pp.make_args(dev, n_iter=a.iters, batch_size=4096, n_samples=64, **dict(c["args"], no_transformation_optimization=bool(a.fixed)))
     torch.manual_seed(0)
     slices, _, _ = simulate_slices(device=dev, **c["sim"])
+    if a.mode == "train":
+        from nesvor_b200.nesvor.fused import attach_render_state, fused_render
+
+        args.no_loss_sync = True
+        inr, out_slices, mask = nb.train(slices, args)
+        rep = {"mode": "train", "fixed": a.fixed, "params_finite": {k: bool(torch.isfinite(v).all()) for k, v in inr.state_dict().items()},
+               "params_absmax": {k: float(v.float().abs().max()) for k, v in inr.state_dict().items()}}
+        grid = pp.phantom_grid(c["sim"]["n"], c["sim"]["res_r"])
+        st = attach_render_state(inr, args)
+        rep["flat16_finite"] = bool(torch.isfinite(st.flat16).all())
+        rec = torch.cat([fused_render(inr, grid[i : i + (1 << 18)].to(dev), None, 0.0, 1).cpu() for i in range(0, grid.shape[0], 1 << 18)])
+        bad = ~torch.isfinite(rec)
+        rep["render_nonfinite"] = int(bad.sum())
+        rep["render_absmax_finite"] = float(rec[~bad].abs().max())
+        if bad.any():
+            idx = bad.nonzero().flatten()[:5]
+            rep["first_bad_points"] = grid[idx].tolist()
+            rep["bbox"] = inr.bounding_box.tolist()
+            x = grid[idx].to(dev)
+            rep["unfused_forward_at_bad_points"] = inr(x[:, None], False).flatten().tolist()
+        print(json.dumps(rep))
+        return
     ds = Dataset(slices, args)
     model = nb.NeSVoR(ds.transformation, ds.resolution, ds.mean, ds.bounding_box, args)
     tr = FusedTrainer(model, args)
