@@ -16,6 +16,7 @@ def main():
     ap.add_argument("--fixed", type=int, default=1)
     ap.add_argument("--iters", type=int, default=3000)
     ap.add_argument("--impl", default="auto")
+    ap.add_argument("--sequence", default="", help="train mode: comma list of `fixed` values run one after the other in THIS process")
     ap.add_argument("--mode", default="step", choices=["step", "train"], help="train: through nesvor_b200.train + the evaluation of psnr_phantom.run_pose_recovery")
     a = ap.parse_args()
     import torch
@@ -33,6 +34,24 @@ def main():
     args = pp.make_args(dev, n_iter=a.iters, batch_size=4096, n_samples=64, **dict(c["args"], no_transformation_optimization=bool(a.fixed)))
     torch.manual_seed(0)
     slices, _, _ = simulate_slices(device=dev, **c["sim"])
+    if a.mode == "train" and a.sequence:
+        reps = []
+        for f in a.sequence.split(","):
+            args = pp.make_args(dev, n_iter=a.iters, batch_size=4096, n_samples=64, no_loss_sync=True, **dict(c["args"], no_transformation_optimization=bool(int(f))))
+            torch.manual_seed(0)
+            slices, volume, _ = simulate_slices(device=dev, **c["sim"])
+            from nesvor_b200.nesvor.fused import attach_render_state, fused_render
+
+            inr, out_slices, mask = nb.train(slices, args)
+            grid = pp.phantom_grid(c["sim"]["n"], c["sim"]["res_r"])
+            st = attach_render_state(inr, args)
+            rec = torch.cat([fused_render(inr, grid[i : i + (1 << 18)].to(dev), None, 0.0, 1).cpu() for i in range(0, grid.shape[0], 1 << 18)])
+            gt = volume[0, 0].reshape(-1).cpu()
+            reps.append({"fixed": int(f), "params_finite": {k: bool(torch.isfinite(v).all()) for k, v in inr.state_dict().items()},
+                         "render_nonfinite": int((~torch.isfinite(rec)).sum()), "gt_nonfinite": int((~torch.isfinite(gt)).sum()),
+                         "psnr_inside": pp.psnr(rec, gt, gt > 0), "n_inside": int((gt > 0).sum()), "rec_absmax": float(rec[torch.isfinite(rec)].abs().max())})
+        print(json.dumps({"mode": "train-sequence", "runs": reps}))
+        return
     if a.mode == "train":
         from nesvor_b200.nesvor.fused import attach_render_state, fused_render
 
