@@ -456,7 +456,10 @@ class FusedTrainer:
         if self.dp_mode == "peer" and getattr(self.args, "dp_sync", None) is None:
             import os
 
-            self.args.dp_sync = os.environ.get("NSV_DP_SYNC", "kernel")  # "kernel" (rendezvous inside the kernel) | "host" (two barriers)
+            # "host": two symmetric-memory barriers around the kernel (default: measured faster at 8 ranks, 0.863 vs 0.896 ms per
+            # step, profiles/r02_bench_8gpu_weak*.json -- every block of the in-kernel variant pays a system-scope fence for
+            # its peer writes); "kernel": the ranks' rendezvous inside the kernel (nsv_adamw_step_dp_sync), equal at 2-4 ranks
+            self.args.dp_sync = os.environ.get("NSV_DP_SYNC", "host")
         if self.dp_mode == "peer" and self.args.dp_sync == "kernel":
             # ONE launch: rendezvous of the ranks (flags in peer memory), reduce-scatter, AdamW, all-gather, rendezvous
             with torch.cuda.device(st.device):

@@ -43,7 +43,7 @@ def main():
         model = nb.NeSVoR(dataset.transformation, dataset.resolution, dataset.mean, dataset.bounding_box, args)
         a = copy.copy(args)
         a.dp_optimizer = "peer" if mode == "peer_host" else mode
-        a.dp_sync = "host" if mode == "peer_host" else "kernel"
+        a.dp_sync = "host" if mode == "peer_host" else "kernel"  # both synchronisation schemes are exercised whatever the default is
         trainers[mode] = FusedTrainer(model, a)
     g = torch.Generator().manual_seed(100 + rank)
     P = dataset.xyz.shape[0]
