@@ -226,6 +226,11 @@ int nsv_set_fused_impl(int impl);
  * (idx_lo, idx_hi, 0, 0) and key (seed_lo, seed_hi) -> Box-Muller.  normals [n,3] f32 and / or raw [n,4] u32 (either may be
  * NULL). */
 int nsv_debug_normal3(uint64_t seed, uint64_t offset, int64_t n, float* normals, uint32_t* raw, void* stream);
+/* 128-sample groups per CTA of the tcgen05 training kernel: 2 (512 threads at 128 registers) or 3 (768 threads at 80
+ * registers, one shared set of TMEM weight-gradient accumulators; only for density-only heads with n_samples <= 128 --
+ * other configurations keep 2); -1 back to the default (env NSV_TC_GROUPS).  Results are identical up to the order of
+ * floating-point accumulation. */
+int nsv_set_fused_tc_groups(int groups);
 /* Tile order of the tcgen05 training kernel: 0 (default; env NSV_TILE_ORDER) tiles strided over the CTAs, 1 one contiguous
  * run of tiles per CTA -- with a spatially ordered batch (Dataset locality_batch_size) a CTA then walks neighbouring pixels
  * of one slice; -1 back to the default.  Results are identical either way (the losses are means over the batch). */
@@ -301,6 +306,10 @@ int nsv_adamw_step_dp_sync(float* param, const void* const* peer_grads, float* e
 /* tcgen05 / TMEM bring-up check used by tests/test_gpu_umma.py: runs every tensor-core operand
  * configuration kernel A uses on fixed 128x64 / 64x64 / 128x16 fp16 inputs (no reference counterpart). */
 int nsv_umma_selftest(const void* A_f16, const void* W_f16, const void* G_f16, float* out, void* stream);
+/* Hardware-behaviour probe behind the 3-group training kernel: `n_issuers` (1..4) threads of different warps each issue
+ * `reps` accumulating M64 N64 K128 products A^T A into ONE TMEM accumulator, unordered; out [64,64] f32 must be
+ * n_issuers * reps * A^T A if accumulating tcgen05.mma instructions of different issuers compose. */
+int nsv_umma_shared_accumulator_test(const void* A_f16, float* out, int n_issuers, int reps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -100,6 +100,8 @@ struct FusedArgs {
   int smem_levels;   // tcgen05 kernel: the first `smem_levels` (dense) levels of the fp16 table are bulk-copied (TMA engine,
                      // cp.async.bulk) into shared memory once per CTA and gathered from there; -1: as many as fit, 0: none
   uint32_t smem_table_bytes;  // set by the launcher: bytes of that table prefix
+  int tc_groups;     // tcgen05 kernel: 128-sample groups per CTA, 2 (512 threads, 128 registers) or 3 (768 threads, 80 registers;
+                     // density-only configurations with n_samples <= 128)
   int tile_order;    // tcgen05 kernel: 0 tiles strided over the CTAs (t, t + 2 grid, ...), 1 a contiguous run of tiles per CTA
                      // (consecutive tiles = consecutive pixels of the batch: pairs with Dataset's locality-aware batch order)
 };

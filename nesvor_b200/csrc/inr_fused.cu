@@ -679,6 +679,7 @@ static long g_agg_max = -1;  // -1: NSV_AGG_MAX or the built-in default
 static int g_fast_path = -1;
 static int g_smem_levels = -2;  // -2: NSV_SMEM_LEVELS or "as many as fit" (-1)
 static int g_tile_order = -1;   // -1: NSV_TILE_ORDER or 0 (strided)
+static int g_tc_groups = -1;    // -1: NSV_TC_GROUPS or the built-in default
 static long long* g_timers = nullptr;
 } }
 
@@ -718,6 +719,12 @@ extern "C" int nsv_debug_normal3(uint64_t seed, uint64_t offset, int64_t n, floa
   const int64_t blocks = (n + 255) / 256;
   nsv::fused::debug_normal3_kernel<<<(int)(blocks < 1184 ? blocks : 1184), 256, 0, (cudaStream_t)stream>>>(seed, offset, n, normals, raw);
   return nsv::check_launch("nsv_debug_normal3");
+}
+
+extern "C" int nsv_set_fused_tc_groups(int groups) {
+  NSV_REQUIRE(groups == -1 || groups == 2 || groups == 3, "nsv_set_fused_tc_groups: 2, 3 or -1 (default)");
+  nsv::fused::g_tc_groups = groups;
+  return NSV_OK;
 }
 
 extern "C" int nsv_set_fused_tile_order(int contiguous) {
@@ -833,6 +840,8 @@ extern "C" int nsv_inr_train_step(const nsv_inr_config* cfg, const nsv_inr_param
     a.smem_table_bytes = 0;
     static const int order_env = getenv("NSV_TILE_ORDER") ? atoi(getenv("NSV_TILE_ORDER")) : 0;
     a.tile_order = g_tile_order >= 0 ? g_tile_order : order_env;
+    static const int groups_env = getenv("NSV_TC_GROUPS") ? atoi(getenv("NSV_TC_GROUPS")) : 2;
+    a.tc_groups = g_tc_groups >= 2 ? g_tc_groups : groups_env;
     a.timers = g_timers;
     a.ablate = getenv("NSV_ABLATE") ? (uint32_t)atoi(getenv("NSV_ABLATE")) : 0u;  // profiling only, tcgen05 kernel
   }

@@ -23,10 +23,19 @@ namespace nsv {
 namespace fused {
 namespace {
 
-constexpr int kW = 64, kGR = 128, kGT = 256, kNGroups = 2;
+constexpr int kW = 64, kGR = 128, kGT = 256;
+// NG = number of 128-sample groups per CTA (256 threads each).  NG = 2: the round-1 kernel (512 threads, 128 registers).
+// NG = 3 (round 2; density-only configurations with n_samples <= 128): 768 threads at 80 registers.  With two groups the MMA
+// chain of one group (17 K cycles per tile, almost all of it latency) is covered by only 8 gather / scatter warps, which
+// reach 75 % of the LSU sector rate; measured, the kernel ran in exactly (LSU time at full rate) + (chain time).  A third
+// group keeps 16 memory warps busy while one group waits on the tensor core.  TMEM has no room for a third set of
+// weight-gradient accumulators next to three forward / dgrad regions (3 x 64 + 3 x 176 > 512 columns), and does not need one:
+// accumulating tcgen05.mma instructions of different issuing threads compose exactly (probed by nsv_umma_shared_accumulator_test,
+// tests/test_gpu_umma.py), so the three groups add into ONE zero-initialised set.
 
-template <int DEPTH, bool SIGMA, bool BIAS = false>
+template <int DEPTH, bool SIGMA, bool BIAS = false, int NG = 2>
 struct TcLayout {
+  static_assert(NG == 2 || (NG == 3 && !SIGMA && !BIAS), "the 3-group kernel is instantiated for the density-only configurations");
   static_assert(!BIAS || (SIGMA && DEPTH == 1), "the fused bias-field head rides on the sigma_net instantiation (depth 1, slice embedding on)");
   // ---- CTA-shared canonical weight tiles (byte offsets) ----
   static constexpr size_t w0 = 0;                                         // [64][32]
@@ -52,16 +61,17 @@ struct TcLayout {
   static constexpr size_t g_bytes = dx + ((alias_dx || BIAS) ? 0 : 128 * 32 * 4);
   // ---- CTA-level fp32 scratch, indexed by CTA row (group * 128 + row) ----
   static constexpr size_t b_groups = (w_end + 127) / 128 * 128;
-  static constexpr size_t b_scr = b_groups + kNGroups * g_bytes;
-  static constexpr size_t fz0 = 0, flv = 256, frho = 512, fxw = 768, fred = 768 + 768, flb = fred + 16 * 16;  // floats
-  static constexpr size_t fend = flb + (BIAS ? 256 : 0);
+  static constexpr size_t b_scr = b_groups + NG * g_bytes;
+  static constexpr size_t nrow = (size_t)NG * 128;  // sample rows per CTA
+  static constexpr size_t fz0 = 0, flv = nrow, frho = 2 * nrow, fxw = 3 * nrow, fred = 6 * nrow, flb = fred + 16 * 16;  // floats
+  static constexpr size_t fend = flb + (BIAS ? nrow : 0);
   static constexpr size_t b_lt = b_scr + fend * 4;
-  static constexpr size_t b_sync = (b_lt + sizeof(LevelTable) + 15) / 16 * 16;  // mbar[2], tmem slot, flags, table mbarrier
+  static constexpr size_t b_sync = (b_lt + sizeof(LevelTable) + 15) / 16 * 16;  // mbar[4] @0, tmem slot @32, grp_ran[4] @40, table mbarrier @56
   static constexpr size_t bytes = (b_sync + 64 + 127) / 128 * 128;
   // [bytes, bytes + staged table bytes): shared-memory copy of the coarsest levels of the fp16 hash table (FusedArgs::smem_levels)
   // ---- TMEM columns ----
   static constexpr uint32_t c_d = 0;                                      // group g: [64 g, 64 g + 64)
-  static constexpr uint32_t c_w0 = 128;                                   // dW0   [64 x 32]
+  static constexpr uint32_t c_w0 = 64 * NG;                               // dW0   [64 x 32]
   static constexpr uint32_t c_wh = c_w0 + 32;                             // dWh_l [64 x 64]
   static constexpr uint32_t c_wo = c_wh + 64 * (DEPTH - 1);               // dWo^T [64 x 16]
   static constexpr uint32_t c_ws0 = c_wo + 16;                            // dWs0  [64 x 32]
@@ -73,7 +83,7 @@ struct TcLayout {
   static_assert(c_end <= (BIAS ? c_d2 : 512), "TMEM columns");
 };
 
-__device__ __forceinline__ void cta_barrier_all() { asm volatile("bar.sync 3, 512;" ::: "memory"); }
+__device__ __forceinline__ void cta_barrier_all() { asm volatile("bar.sync 4, 512;" ::: "memory"); }  // 2-group kernel only (S = 256)
 
 // ---- epilogues: this thread owns TMEM lane (= sample row) `row` and 32 accumulator columns starting at c0 ----
 __device__ __forceinline__ void epi_relu_store(uint32_t taddr, unsigned char* tile, int row, int c0) {
@@ -119,9 +129,10 @@ __device__ __forceinline__ void epi_mask_store(uint32_t taddr, unsigned char* ti
 // TIMED (profiling builds only, a.timers != NULL): every warp accumulates the clock cycles it spends per phase
 // (0 geometry + gather, 1 publish / group barriers, 2 MMA issue -> mbarrier wait, 3 epilogues, 4 render + losses,
 //  5 scatter, 6 pixel barrier) and adds them to a.timers[phase] at the end
-template <int DEPTH, bool SIGMA, bool TIMED = false, bool BIAS = false>
-__global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_constant__ FusedArgs a) {
-  using L = TcLayout<DEPTH, SIGMA, BIAS>;
+template <int DEPTH, bool SIGMA, bool TIMED = false, bool BIAS = false, int NG = 2>
+__global__ void __launch_bounds__(256 * NG, 1) inr_train_tc_kernel(const __grid_constant__ FusedArgs a) {
+  using L = TcLayout<DEPTH, SIGMA, BIAS, NG>;
+  constexpr int kNGroups = NG, kThreads = 256 * NG;
   long long t_acc[TIMED ? 8 : 1] = {};
   long long t_last = TIMED ? clock64() : 0;
   auto tick = [&](int seg) {
@@ -143,9 +154,9 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
   float* sf = reinterpret_cast<float*>(smem + L::b_scr);
   LevelTable& lt = *reinterpret_cast<LevelTable*>(smem + L::b_lt);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + L::b_sync) + grp;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::b_sync + 16);
-  uint32_t* grp_ran = reinterpret_cast<uint32_t*>(smem + L::b_sync + 24);
-  uint64_t* tbar = reinterpret_cast<uint64_t*>(smem + L::b_sync + 32);  // completion of the staged-table bulk copy
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::b_sync + 32);
+  uint32_t* grp_ran = reinterpret_cast<uint32_t*>(smem + L::b_sync + 40);
+  uint64_t* tbar = reinterpret_cast<uint64_t*>(smem + L::b_sync + 56);  // completion of the staged-table bulk copy
   const nsv_inr_config& cfg = a.cfg;
   // TMA-staged table prefix: levels [0, smem_levels) are contiguous at the start of the flat fp16 table (level-major tcnn
   // layout, every level a multiple of 8 entries = 32 bytes), so ONE bulk copy per CTA brings them into shared memory
@@ -172,11 +183,10 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
       lt.tbl[tid] = reinterpret_cast<const __half2*>(smem + L::bytes) + lt.offset[tid];
     if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
-      umma::mbar_init(reinterpret_cast<uint64_t*>(smem + L::b_sync), 1);
-      umma::mbar_init(reinterpret_cast<uint64_t*>(smem + L::b_sync) + 1, 1);
+      for (int g = 0; g < NG; ++g) umma::mbar_init(reinterpret_cast<uint64_t*>(smem + L::b_sync) + g, 1);
       umma::mbar_init(tbar, 1);
       umma::mbar_fence_init();
-      grp_ran[0] = grp_ran[1] = 0;
+      for (int g = 0; g < 4; ++g) grp_ran[g] = 0;
       if (stab_bytes) {  // in flight while the CTA stages its weights; waited for before the first gather
         umma::mbar_expect_tx(tbar, stab_bytes);
         for (uint32_t o = 0; o < stab_bytes; o += 32768u)
@@ -203,11 +213,20 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
   const uint32_t tm = *tmem_slot;
   const uint32_t td = tm + L::c_d + 64u * grp;                       // this group's forward / dgrad region
   const uint32_t td2 = tm + L::c_d2 + 64u * grp;                     // BIAS: second region, so that b_net's products ride in the same MMA rounds
-  const uint32_t tacc = tm + ((16u * grp) << 16);                    // this group's wgrad accumulators (lane offset)
+  // wgrad accumulators: NG = 2 each group its own (TMEM lane offset 16 g); NG = 3 ONE set shared by all groups (lane offset 0)
+  const uint32_t tacc = NG == 3 ? tm : tm + ((16u * grp) << 16);
   const uint32_t tlane = (uint32_t)(32 * q4) << 16;                  // epilogue lane quarter
   const bool issuer = (gw == 0 && lane == 0);
   uint32_t ph = 0;                                                   // mbarrier phase parity
-  uint32_t acc_on = 0;                                               // 0 on the group's first tile: wgrad MMAs overwrite
+  uint32_t acc_on = NG == 3 ? 1u : 0u;                               // NG = 2: 0 on the group's first tile (wgrad MMAs overwrite)
+  if (NG == 3) {  // the shared accumulators start from zero: every warp clears the columns of its own lane quarter
+    const uint32_t tq0 = tm + ((uint32_t)(32 * (warp & 3)) << 16);
+    for (uint32_t c = L::c_w0 + 16 * (uint32_t)(warp >> 2); c < L::c_end; c += 16 * (kThreads / 128)) umma::tmem_st16_fill(tq0 + c, 0u);
+    umma::tmem_st_wait();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+  }
 
   const uint32_t s_w0 = umma::saddr(wt + L::w0), s_wh = umma::saddr(wt + L::wh), s_wo = umma::saddr(wt + L::wo);
   const uint32_t s_ws0 = umma::saddr(wt + L::ws0), s_wso = umma::saddr(wt + L::wso);
@@ -687,17 +706,18 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
   __syncthreads();
   umma::fence_after_sync();
   {
-    // lanes [0,16) of a quarter hold group 0's accumulator rows 16 q4 + lane, lanes [16,32) group 1's
-    const int q = warp & 3, part = warp >> 2;  // 4 column partitions across the 16 warps
+    // NG = 2: lanes [0,16) of a quarter hold group 0's accumulator rows 16 q4 + lane, lanes [16,32) group 1's;
+    // NG = 3: lanes [0,16) hold the shared accumulators, lanes [16,32) nothing
+    const int q = warp & 3, part = warp >> 2;  // kThreads / 128 column partitions across the warps
     const int arow = 16 * q + (lane & 15), agrp = lane >> 4;
-    const bool live = grp_ran[agrp] != 0;
+    const bool live = NG == 3 ? (agrp == 0 && (grp_ran[0] | grp_ran[1] | grp_ran[2]) != 0) : grp_ran[agrp] != 0;
     const uint32_t tq = tm + ((uint32_t)(32 * q) << 16);
     float* gd = a.g_mlp + a.off_density;
     float* gs = a.g_mlp + a.off_sigma;
     int chunk = 0;
     auto flush = [&](uint32_t col, int ncols, float* dst, int ld, bool transposed) {
       for (int c0 = 0; c0 < ncols; c0 += 16, ++chunk) {
-        if ((chunk & 3) != part) continue;
+        if ((chunk % (kThreads / 128)) != part) continue;
         uint32_t d[16];
         umma::tmem_ld16(tq + col + c0, d);
         umma::tmem_ld_wait();
@@ -735,9 +755,10 @@ __global__ void __launch_bounds__(kThreads, 1) inr_train_tc_kernel(const __grid_
   if (warp == 0) umma::tmem_dealloc(tm, 512);
 }
 
-template <int DEPTH, bool SIGMA, bool BIAS = false>
+template <int DEPTH, bool SIGMA, bool BIAS = false, int NG = 2>
 int launch_tc(const FusedArgs& a_in, cudaStream_t st) {
-  using L = TcLayout<DEPTH, SIGMA, BIAS>;
+  using L = TcLayout<DEPTH, SIGMA, BIAS, NG>;
+  constexpr int kNGroups = NG, kThreads = 256 * NG;
   static_assert(L::bytes <= 227 * 1024, "shared memory");
   // N1 (north star: "TMA-staged hash tables in shared memory"): as many leading DENSE levels as fit beside the tiles
   FusedArgs a = a_in;
@@ -754,18 +775,18 @@ int launch_tc(const FusedArgs& a_in, cudaStream_t st) {
   }
   a.smem_table_bytes = a.smem_levels > 0 ? a.cfg.grid.offset[a.smem_levels] * 4u : 0u;
   const size_t smem_total = L::bytes + a.smem_table_bytes;
-  cudaError_t e = cudaFuncSetAttribute(inr_train_tc_kernel<DEPTH, SIGMA, false, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total);
+  cudaError_t e = cudaFuncSetAttribute(inr_train_tc_kernel<DEPTH, SIGMA, false, BIAS, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total);
   if (e != cudaSuccess) {
     set_error("nsv_inr_train_step(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return (int)e;
   }
   const int64_t ctas = (a.B * (int64_t)a.S / kGR + kNGroups - 1) / kNGroups;
   const int grid = (int)(ctas < num_sms() ? ctas : num_sms());
-  if (a.timers && DEPTH == 3 && !SIGMA) {  // profiling build of the config-2 instantiation
+  if (a.timers && DEPTH == 3 && !SIGMA && NG == 2) {  // profiling build of the config-2 instantiation
     cudaFuncSetAttribute(inr_train_tc_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total);
     inr_train_tc_kernel<3, false, true><<<grid, kThreads, smem_total, st>>>(a);
   } else {
-    inr_train_tc_kernel<DEPTH, SIGMA, false, BIAS><<<grid, kThreads, smem_total, st>>>(a);
+    inr_train_tc_kernel<DEPTH, SIGMA, false, BIAS, NG><<<grid, kThreads, smem_total, st>>>(a);
   }
   if (int err = check_launch("nsv_inr_train_step(tcgen05)")) return err;
   inr_finalize_kernel<<<1, 256, 0, st>>>(a.logit_coef, a.g_c, a.losses, a.n_slices, a.cfg.slice_scale, a.cfg.image_reg, a.cfg.delta,
@@ -778,7 +799,7 @@ int launch_tc(const FusedArgs& a_in, cudaStream_t st) {
 int launch_train_tc(const FusedArgs& a, cudaStream_t st) {
   const nsv_inr_config& c = a.cfg;
   // 256-sample pixels span both groups of a CTA: they must march through the same tiles
-  if (c.width != kW || c.depth < 1 || c.depth > 3 || (c.pixel_variance && c.depth != 1) || (a.B * (int64_t)a.S) % (kGR * kNGroups) != 0) {
+  if (c.width != kW || c.depth < 1 || c.depth > 3 || (c.pixel_variance && c.depth != 1) || (a.B * (int64_t)a.S) % (kGR * 2) != 0) {
     set_error("nsv_inr_train_step: no tcgen05 instantiation for width=%d depth=%d (needs width 64, depth 1..3, B*S %% 256 == 0)", c.width, c.depth);
     return NSV_EUNSUPPORTED;
   }
@@ -790,6 +811,11 @@ int launch_train_tc(const FusedArgs& a, cudaStream_t st) {
     return launch_tc<1, true, true>(a, st);
   }
   if (c.pixel_variance) return launch_tc<1, true>(a, st);
+  if (a.tc_groups == 3 && a.S <= kGR && !a.timers) {  // three 128-sample groups per CTA: density-only heads, pixels of <= 128 samples
+    if (c.depth == 1) return launch_tc<1, false, false, 3>(a, st);
+    if (c.depth == 2) return launch_tc<2, false, false, 3>(a, st);
+    return launch_tc<3, false, false, 3>(a, st);
+  }
   if (c.depth == 1) return launch_tc<1, false>(a, st);
   if (c.depth == 2) return launch_tc<2, false>(a, st);
   return launch_tc<3, false>(a, st);

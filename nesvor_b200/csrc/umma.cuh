@@ -115,6 +115,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> TMEM: 16 consecutive 32-bit columns of the caller's own TMEM lane, all set to `v`
+__device__ __forceinline__ void tmem_st16_fill(uint32_t taddr, uint32_t v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(v)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // cooperative copy: row-major global [rows][cols] fp16 -> canonical shared tile (16-byte chunks)
 __device__ __forceinline__ void stage_tile(unsigned char* tile, const __half* __restrict__ src, int rows, int cols, int tid, int nthreads) {

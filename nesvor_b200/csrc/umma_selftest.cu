@@ -150,8 +150,64 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const __half* __r
   if (warp == 0) umma::tmem_dealloc(tm, 512);
 }
 
+// Do accumulating MMAs issued by DIFFERENT threads into the SAME TMEM accumulator compose?  `n_issuers` warps' lane 0 each
+// issue `reps` x (A^T A, M64 N64 K128 = 8 instructions, accumulate on) into one zero-initialised D without any ordering
+// between them; every issuer commits to its own mbarrier.  out [64,64] must equal n_issuers * reps * A^T A.
+__global__ void __launch_bounds__(128, 1) umma_shared_acc_kernel(const __half* __restrict__ A, float* __restrict__ out, int n_issuers, int reps) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* tA = smem;  // [128][64]
+  __shared__ uint64_t mbar[4];
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  umma::stage_tile(tA, A, 128, 64, tid, 128);
+  if (warp == 0) umma::tmem_alloc(&tmem_base_slot, 64);
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) umma::mbar_init(&mbar[i], 1);
+    umma::mbar_fence_init();
+  }
+  umma::fence_smem_to_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tm = tmem_base_slot;
+  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  for (int c0 = 0; c0 < 64; c0 += 16) umma::tmem_st16_fill(tm + lane_addr + c0, 0u);
+  umma::tmem_st_wait();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  if (lane == 0 && warp < n_issuers) {
+    const uint32_t RG64 = 8 * 128;
+    for (int rep = 0; rep < reps; ++rep)
+      for (int k = 0; k < 8; ++k)
+        umma::mma_f16(tm, umma::smem_desc(umma::saddr(tA) + k * 2 * RG64, RG64, 128), umma::smem_desc(umma::saddr(tA) + k * 2 * RG64, RG64, 128),
+                      umma::instr_desc(64, 64, true, true), 1u);
+    umma::commit(&mbar[warp]);
+  }
+  for (int i = 0; i < n_issuers; ++i) umma::mbar_wait(&mbar[i], 0);
+  umma::fence_after_sync();
+  uint32_t r[32];
+  const int row = 16 * warp + (lane & 15);
+  for (int c0 = 0; c0 < 64; c0 += 32) {
+    umma::tmem_ld32(tm + lane_addr + c0, r);
+    umma::tmem_ld_wait();
+    if (lane < 16)
+      for (int c = 0; c < 32; ++c) out[(size_t)row * 64 + c0 + c] = __uint_as_float(r[c]);
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tm, 64);
+}
+
 }  // namespace
 }  // namespace nsv
+
+extern "C" int nsv_umma_shared_accumulator_test(const void* A, float* out, int n_issuers, int reps, void* stream) {
+  using namespace nsv;
+  NSV_REQUIRE(A && out && n_issuers >= 1 && n_issuers <= 4 && reps >= 1, "nsv_umma_shared_accumulator_test: bad arguments");
+  umma_shared_acc_kernel<<<1, 128, 128 * 64 * 2 + 128, (cudaStream_t)stream>>>((const __half*)A, out, n_issuers, reps);
+  return check_launch("nsv_umma_shared_accumulator_test");
+}
 
 // A [128,64], W [64,64], G [128,16] fp16 row-major; out: 128*64*4 + 64*64*2 + 128*16 + 64*16 + 128*32 + 64*32 floats
 extern "C" int nsv_umma_selftest(const void* A, const void* W, const void* G, float* out, void* stream) {

@@ -110,19 +110,24 @@ CONFIGS = {
 
 @pytest.fixture
 def fused_impl(request):
+    """"tcgen05x3" = the tcgen05 all-phases kernel with three 128-sample groups per CTA (768 threads, shared TMEM weight-gradient
+    accumulators); it serves the density-only configurations with n_samples <= 128 and silently stays at two groups elsewhere."""
     from nesvor_b200 import _lib
 
-    _lib.set_fused_impl(request.param)
-    yield request.param
+    name = request.param
+    _lib.set_fused_impl("tcgen05" if name == "tcgen05x3" else name)
+    _lib.check(_lib.lib().nsv_set_fused_tc_groups(3 if name == "tcgen05x3" else 2))
+    yield name
     _lib.set_fused_impl("auto")
+    _lib.check(_lib.lib().nsv_set_fused_tc_groups(-1))
 
 
-@pytest.mark.parametrize("fused_impl", ["mma", "tcgen05", "ws"], indirect=True)
+@pytest.mark.parametrize("fused_impl", ["mma", "tcgen05", "tcgen05x3", "ws"], indirect=True)
 @pytest.mark.parametrize("name", list(CONFIGS))
 def test_fused_train_step_parity(native_lib, name, fused_impl):
     from nesvor_b200.nesvor.fused import FusedState
 
-    if fused_impl in ("tcgen05", "ws") and CONFIGS[name].get("width", 64) != 64:
+    if fused_impl in ("tcgen05", "tcgen05x3", "ws") and CONFIGS[name].get("width", 64) != 64:
         pytest.skip("tcgen05 paths are instantiated for width 64 (UMMA M = 64 wgrad)")
     if fused_impl in ("mma", "ws") and CONFIGS[name].get("n_levels_bias", 0):
         pytest.skip("the bias-field head is instantiated in the tcgen05 all-phases kernel only")

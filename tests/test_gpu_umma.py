@@ -42,3 +42,23 @@ def test_umma_operand_layouts(native_lib):
         if not (err < 2e-3 * max(1.0, float(ref.abs().max()))):
             bad.append(name)
     assert not bad, bad
+
+
+@pytest.mark.parametrize("n_issuers,reps", [(1, 1), (1, 50), (2, 200), (3, 400), (4, 1000)])
+def test_accumulating_mma_of_different_issuers_compose(native_lib, n_issuers, reps):
+    """Hardware-behaviour probe the 3-group training kernel rests on: its three groups' issuing threads accumulate their
+    weight-gradient products (M64 N64 K128, accumulate on) into ONE set of TMEM accumulators, unordered.  With exactly
+    representable addends (small integers) every order of accumulation gives the same fp32 sum, so the result must be
+    EXACTLY n_issuers * reps * A^T A -- a lost or torn update would show as a smaller count."""
+    from nesvor_b200 import _lib
+
+    g = torch.Generator().manual_seed(n_issuers * 1000 + reps)
+    A = torch.randint(-2, 3, (128, 64), generator=g).half().cuda()  # integers: every partial sum stays exact in fp32 (< 2^24)
+    out = torch.full((64, 64), float("nan"), device="cuda")
+    for _ in range(5):  # a few launches: the interleaving of the issuers changes from run to run
+        out.fill_(float("nan"))
+        _lib.check(native_lib.nsv_umma_shared_accumulator_test(_lib.ptr(A), _lib.ptr(out), ctypes.c_int(n_issuers), ctypes.c_int(reps), _lib.stream()))
+        torch.cuda.synchronize()
+        want = (A.float().t() @ A.float()) * (n_issuers * reps)
+        assert float(want.abs().max()) < 2**24
+        assert torch.equal(out, want), (n_issuers, reps, float((out - want).abs().max()))

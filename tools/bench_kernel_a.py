@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--cfg", type=int, default=2)
     ap.add_argument("--impl", default="auto")
     ap.add_argument("--ablate", default="0", help="comma list of NSV_ABLATE masks (1: no table loads, 2: no table reductions, 4: no MLP chain)")
+    ap.add_argument("--groups", default="-1", help="comma list of nsv_set_fused_tc_groups values (2, 3, -1 default)")
     ap.add_argument("--locality", default="0", help="comma list: 0 random order inside the batch + strided tiles, 1 (slice, y, x)-ordered batch + contiguous tiles per CTA")
     ap.add_argument("--timers", action="store_true", help="per-phase warp-cycle breakdown of the tcgen05 kernel (profiling build)")
     a = ap.parse_args()
@@ -66,8 +67,9 @@ def main():
     key = (batch["slice_idx"].long() << 26) | (((batch["xyz"][:, 1] - dataset.xyz[:, 1].min()).round().long().clamp(0, 8191)) << 13) | (batch["xyz"][:, 0] - dataset.xyz[:, 0].min()).round().long().clamp(0, 8191)
     order = torch.argsort(key)
     batch_sorted = {k: v[order].contiguous() for k, v in batch.items()}
-    for var in [(v, ab, loc) for v in a.variants.split(",") for ab in a.ablate.split(",") for loc in a.locality.split(",")]:
-        var, ablate, loc = var
+    for var in [(v, ab, loc, gr) for v in a.variants.split(",") for ab in a.ablate.split(",") for loc in a.locality.split(",") for gr in a.groups.split(",")]:
+        var, ablate, loc, gr = var
+        _lib.check(_lib.lib().nsv_set_fused_tc_groups(int(gr)))
         batch = batch_sorted if int(loc) else batch_random
         _lib.lib().nsv_set_fused_tile_order(int(loc))
         os.environ["NSV_ABLATE"] = ablate
@@ -86,11 +88,12 @@ def main():
             torch.cuda.synchronize()
             if i >= 3:
                 durs.append(k0.elapsed_time(k1))
-        print(json.dumps({"cfg": a.cfg, "impl": a.impl, "agg_max": agg, "fast": fast, "smem_levels": smem, "locality": int(loc), "ablate": int(ablate), "ms_mean": sum(durs) / len(durs), "ms_min": min(durs),
+        print(json.dumps({"cfg": a.cfg, "impl": a.impl, "agg_max": agg, "fast": fast, "smem_levels": smem, "locality": int(loc), "groups": int(gr), "ablate": int(ablate), "ms_mean": sum(durs) / len(durs), "ms_min": min(durs),
                           "gq_per_s": B * S / (min(durs) * 1e-3) / 1e9}), flush=True)
     _lib.set_fused_tuning(-1, -1)
     _lib.lib().nsv_set_fused_smem_levels(-2)
     _lib.lib().nsv_set_fused_tile_order(-1)
+    _lib.lib().nsv_set_fused_tc_groups(-1)
     batch = batch_random
     if args.n_levels_bias:  # the mean(log_bias) pre-pass alone (part of every forward_backward timed above)
         import ctypes
