@@ -211,12 +211,21 @@ __global__ void __launch_bounds__(256 * NG, 1) inr_train_tc_kernel(const __grid_
   umma::fence_after_sync();
   if (stab_bytes) umma::mbar_wait(tbar, 0);
   const uint32_t tm = *tmem_slot;
-  const uint32_t td = tm + L::c_d + 64u * grp;                       // this group's forward / dgrad region
-  const uint32_t td2 = tm + L::c_d2 + 64u * grp;                     // BIAS: second region, so that b_net's products ride in the same MMA rounds
   // wgrad accumulators: NG = 2 each group its own (TMEM lane offset 16 g); NG = 3 ONE set shared by all groups (lane offset 0)
-  const uint32_t tacc = NG == 3 ? tm : tm + ((16u * grp) << 16);
   const uint32_t tlane = (uint32_t)(32 * q4) << 16;                  // epilogue lane quarter
-  const bool issuer = (gw == 0 && lane == 0);
+  // MMA issue: the whole first warp of the group enters the issuing regions (warp-uniform branch) and one elected lane issues;
+  // everything the MMAs take as operands is derived from lane 0's values through shuffles, so that ptxas keeps it in uniform
+  // registers (see umma::mma_f16_elect)
+  const int grp_u = __shfl_sync(0xffffffffu, grp, 0);
+  const bool issuer = __shfl_sync(0xffffffffu, gw, 0) == 0;
+  const uint32_t smem_u = __shfl_sync(0xffffffffu, umma::saddr(smem), 0);
+  const uint32_t tm_u = __shfl_sync(0xffffffffu, tm, 0);
+  const uint32_t wt_u = smem_u, gt_u = smem_u + (uint32_t)L::b_groups + (uint32_t)grp_u * (uint32_t)L::g_bytes;
+  const uint32_t mbar_u = smem_u + (uint32_t)L::b_sync + 8u * (uint32_t)grp_u;
+  const uint32_t td = tm_u + L::c_d + 64u * grp_u;    // this group's forward / dgrad region
+  const uint32_t td2 = tm_u + L::c_d2 + 64u * grp_u;  // BIAS: second region, so that b_net's products ride in the same MMA rounds
+  // wgrad accumulators: NG = 2 each group its own (TMEM lane offset 16 g); NG = 3 ONE set shared by all groups (lane offset 0)
+  const uint32_t tacc = NG == 3 ? tm_u : tm_u + ((16u * grp_u) << 16);
   uint32_t ph = 0;                                                   // mbarrier phase parity
   uint32_t acc_on = NG == 3 ? 1u : 0u;                               // NG = 2: 0 on the group's first tile (wgrad MMAs overwrite)
   if (NG == 3) {  // the shared accumulators start from zero: every warp clears the columns of its own lane quarter
@@ -228,34 +237,35 @@ __global__ void __launch_bounds__(256 * NG, 1) inr_train_tc_kernel(const __grid_
     umma::fence_after_sync();
   }
 
-  const uint32_t s_w0 = umma::saddr(wt + L::w0), s_wh = umma::saddr(wt + L::wh), s_wo = umma::saddr(wt + L::wo);
-  const uint32_t s_ws0 = umma::saddr(wt + L::ws0), s_wso = umma::saddr(wt + L::wso);
-  const uint32_t s_tx = umma::saddr(gt + L::tx), s_th = umma::saddr(gt + L::th), s_tg = umma::saddr(gt + L::tg);
-  const uint32_t s_tsx = umma::saddr(gt + L::tsx), s_tsh = umma::saddr(gt + L::tsh);
-  const uint32_t s_wb0 = umma::saddr(wt + L::wb0), s_wbo = umma::saddr(wt + L::wbo);
-  const uint32_t s_tbx = umma::saddr(gt + L::tbx), s_tbh = umma::saddr(gt + L::tbh), s_tgb = umma::saddr(gt + L::tgb);
+  const uint32_t s_w0 = wt_u + (uint32_t)L::w0, s_wh = wt_u + (uint32_t)L::wh, s_wo = wt_u + (uint32_t)L::wo;
+  const uint32_t s_ws0 = wt_u + (uint32_t)L::ws0, s_wso = wt_u + (uint32_t)L::wso;
+  const uint32_t s_tx = gt_u + (uint32_t)L::tx, s_th = gt_u + (uint32_t)L::th, s_tg = gt_u + (uint32_t)L::tg;
+  const uint32_t s_tsx = gt_u + (uint32_t)L::tsx, s_tsh = gt_u + (uint32_t)L::tsh;
+  const uint32_t s_wb0 = wt_u + (uint32_t)L::wb0, s_wbo = wt_u + (uint32_t)L::wbo;
+  const uint32_t s_tbx = gt_u + (uint32_t)L::tbx, s_tbh = gt_u + (uint32_t)L::tbh, s_tgb = gt_u + (uint32_t)L::tgb;
   // batch mean of log_bias (biasReg = mean^2, models.py:323), produced by nsv_inr_bias_mean before this launch
   const float bias_mean = BIAS ? __ldg(a.losses + 4) : 0.f;
   constexpr uint32_t RG64 = 8 * 128, RG32 = 4 * 128, RG16 = 2 * 128;  // byte stride between 8-row groups of a tile
   // forward: D[128 x N] = A[128 x K] W[N x K]^T  (A, W K-major)
   auto mma_fwd_d = [&](uint32_t d, uint32_t s_a, uint32_t rg_a, uint32_t s_w, uint32_t rg_w, int K, int N) {
     for (int k = 0; k < K / 16; ++k)
-      umma::mma_f16(d, umma::smem_desc(s_a + k * 256, 128, rg_a), umma::smem_desc(s_w + k * 256, 128, rg_w),
-                    umma::instr_desc(128, N, false, false), k > 0);
+      umma::mma_f16_elect(d, umma::smem_desc(s_a + k * 256, 128, rg_a), umma::smem_desc(s_w + k * 256, 128, rg_w),
+                          umma::instr_desc(128, N, false, false), k > 0);
   };
   auto mma_fwd = [&](uint32_t s_a, uint32_t rg_a, uint32_t s_w, uint32_t rg_w, int K, int N) { mma_fwd_d(td, s_a, rg_a, s_w, rg_w, K, N); };
   // dgrad: D[128 x N] = dC[128 x K] W[K x N]  (W tile as MN-major B)
   auto mma_dgrad_d = [&](uint32_t d, uint32_t s_dc, uint32_t rg_dc, uint32_t s_w, uint32_t rg_w, int K, int N) {
     for (int k = 0; k < K / 16; ++k)
-      umma::mma_f16(d, umma::smem_desc(s_dc + k * 256, 128, rg_dc), umma::smem_desc(s_w + k * 2 * rg_w, rg_w, 128),
-                    umma::instr_desc(128, N, false, true), k > 0);
+      umma::mma_f16_elect(d, umma::smem_desc(s_dc + k * 256, 128, rg_dc), umma::smem_desc(s_w + k * 2 * rg_w, rg_w, 128),
+                          umma::instr_desc(128, N, false, true), k > 0);
   };
   auto mma_dgrad = [&](uint32_t s_dc, uint32_t rg_dc, uint32_t s_w, uint32_t rg_w, int K, int N) { mma_dgrad_d(td, s_dc, rg_dc, s_w, rg_w, K, N); };
   // wgrad: acc[64 x N] += P[128 x 64]^T Q[128 x N]  (both tiles MN-major, K = the 128 sample rows)
   auto mma_wgrad = [&](uint32_t col, uint32_t s_p, uint32_t s_q, uint32_t rg_q, int N) {
+    const uint32_t acc_u = __shfl_sync(0xffffffffu, acc_on, 0);
     for (int k = 0; k < kGR / 16; ++k)
-      umma::mma_f16(tacc + col, umma::smem_desc(s_p + k * 2 * RG64, RG64, 128), umma::smem_desc(s_q + k * 2 * rg_q, rg_q, 128),
-                    umma::instr_desc(64, N, true, true), acc_on | (uint32_t)(k > 0));
+      umma::mma_f16_elect(tacc + col, umma::smem_desc(s_p + k * 2 * RG64, RG64, 128), umma::smem_desc(s_q + k * 2 * rg_q, rg_q, 128),
+                          umma::instr_desc(64, N, true, true), acc_u | (uint32_t)(k > 0));
   };
   // writers publish their shared-memory stores to the tensor core, then the group meets
   auto publish = [&]() {
@@ -351,7 +361,7 @@ __global__ void __launch_bounds__(256 * NG, 1) inr_train_tc_kernel(const __grid_
       umma::fence_after_sync();
       mma_fwd(s_tx, RG32, s_w0, RG32, 32, 64);
       if (BIAS) mma_fwd_d(td2, s_tbx, RG32, s_wb0, RG32, 32, 64);
-      umma::commit(mbar);
+      umma::commit_elect(mbar_u);
     }
     wait_mma();
     epi_relu_store(td + tlane + 32 * half, gt + L::th, erow, 32 * half);
@@ -362,7 +372,7 @@ __global__ void __launch_bounds__(256 * NG, 1) inr_train_tc_kernel(const __grid_
       if (issuer) {
         umma::fence_after_sync();
         mma_fwd(s_th + (l - 1) * 128 * 64 * 2, RG64, s_wh + (l - 1) * 64 * 64 * 2, RG64, 64, 64);
-        umma::commit(mbar);
+        umma::commit_elect(mbar_u);
       }
       wait_mma();
       epi_relu_store(td + tlane + 32 * half, gt + L::th + (size_t)l * 128 * 64 * 2, erow, 32 * half);
@@ -372,7 +382,7 @@ __global__ void __launch_bounds__(256 * NG, 1) inr_train_tc_kernel(const __grid_
       umma::fence_after_sync();
       mma_fwd(s_th + (DEPTH - 1) * 128 * 64 * 2, RG64, s_wo, RG64, 64, 16);
       if (BIAS) mma_fwd_d(td2, s_tbh, RG64, s_wbo, RG64, 64, 16);
-      umma::commit(mbar);
+      umma::commit_elect(mbar_u);
     }
     wait_mma();
     if (half == 0) {  // z[0..15] of row erow
@@ -419,7 +429,7 @@ __global__ void __launch_bounds__(256 * NG, 1) inr_train_tc_kernel(const __grid_
       if (issuer) {
         umma::fence_after_sync();
         mma_fwd(s_tsx, RG32, s_ws0, RG32, 32, 64);
-        umma::commit(mbar);
+        umma::commit_elect(mbar_u);
       }
       wait_mma();
       epi_relu_store(td + tlane + 32 * half, gt + L::tsh, erow, 32 * half);
@@ -427,7 +437,7 @@ __global__ void __launch_bounds__(256 * NG, 1) inr_train_tc_kernel(const __grid_
       if (issuer) {
         umma::fence_after_sync();
         mma_fwd(s_tsh, RG64, s_wso, RG64, 64, 16);
-        umma::commit(mbar);
+        umma::commit_elect(mbar_u);
       }
       wait_mma();
       if (half == 0) {
@@ -544,7 +554,7 @@ __global__ void __launch_bounds__(256 * NG, 1) inr_train_tc_kernel(const __grid_
           mma_wgrad(L::c_wbo, s_tbh, s_tgb, RG16, 16);            // dWbo^T += Hb^T Gb
           mma_dgrad_d(td2, s_tgb, RG16, s_wbo, RG64, 16, 64);     // dHb = Gb Wbo
         }
-        umma::commit(mbar);
+        umma::commit_elect(mbar_u);
       }
       wait_mma();
       epi_mask_store(td + tlane + 32 * half, gt + L::tsh, erow, 32 * half);
@@ -558,7 +568,7 @@ __global__ void __launch_bounds__(256 * NG, 1) inr_train_tc_kernel(const __grid_
           mma_wgrad(L::c_wb0, s_tbh, s_tbx, RG32, 32);            // dWb0 += dZb^T [se | pe_bias | 0]
           mma_dgrad_d(td2, s_tbh, RG64, s_wb0, RG32, 64, 32);     // d[se | pe_bias | 0] = dZb Wb0
         }
-        umma::commit(mbar);
+        umma::commit_elect(mbar_u);
       }
       wait_mma();
       {
@@ -610,7 +620,7 @@ __global__ void __launch_bounds__(256 * NG, 1) inr_train_tc_kernel(const __grid_
         umma::fence_after_sync();
         mma_wgrad(L::c_wo, s_hl, s_tg, RG16, 16);          // dWo^T += H_last^T G
         mma_dgrad(s_tg, RG16, s_wo, RG64, 16, 64);          // dH_last = G Wo
-        umma::commit(mbar);
+        umma::commit_elect(mbar_u);
       }
       wait_mma();
       epi_mask_store(td + tlane + 32 * half, gt + L::th + (size_t)(DEPTH - 1) * 128 * 64 * 2, erow, 32 * half);
@@ -623,7 +633,7 @@ __global__ void __launch_bounds__(256 * NG, 1) inr_train_tc_kernel(const __grid_
         umma::fence_after_sync();
         mma_wgrad(L::c_wh + 64 * (l - 1), s_dz, s_hp, RG64, 64);          // dWh_{l-1} += dZ_l^T H_{l-1}
         mma_dgrad(s_dz, RG64, s_wh + (l - 1) * 64 * 64 * 2, RG64, 64, 64);  // dH_{l-1} = dZ_l Wh_{l-1}
-        umma::commit(mbar);
+        umma::commit_elect(mbar_u);
       }
       wait_mma();
       epi_mask_store(td + tlane + 32 * half, gt + L::th + (size_t)(l - 1) * 128 * 64 * 2, erow, 32 * half);
@@ -633,7 +643,7 @@ __global__ void __launch_bounds__(256 * NG, 1) inr_train_tc_kernel(const __grid_
       umma::fence_after_sync();
       mma_wgrad(L::c_w0, s_th, s_tx, RG32, 32);            // dW0 += dZ_0^T X
       mma_dgrad(s_th, RG64, s_w0, RG32, 64, 32);           // dX = dZ_0 W0
-      umma::commit(mbar);
+      umma::commit_elect(mbar_u);
     }
     wait_mma();
     }
