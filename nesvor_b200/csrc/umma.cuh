@@ -44,27 +44,6 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_
       : "memory");
 }
 
-// The same, issued from a WARP-UNIFORM region by one elected lane.  tcgen05.mma takes its descriptors, the TMEM address
-// and the accumulate predicate from UNIFORM registers: when the operands are per-thread values (the issuing code sits
-// behind a `lane == 0` branch) ptxas wraps every instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop -- ~20
-// dependent instructions per MMA, which made the 8-12 MMAs of a layer step take longer to ISSUE than to execute (the
-// "MMA issue -> mbarrier" idle time of profiles/r01_phase_breakdown.md).  With warp-uniform operands (derived through
-// __shfl_sync from lane 0) and the election inside the asm, the values live in uniform registers and an MMA is 3-4
-// instructions.
-__device__ __forceinline__ void mma_f16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void commit_elect(uint32_t mbar_saddr) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(mbar_saddr)
-      : "memory");
-}
-
 // arrive on an mbarrier when every previously issued MMA of this thread has completed
 __device__ __forceinline__ void commit(uint64_t* mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(saddr(mbar)) : "memory");
