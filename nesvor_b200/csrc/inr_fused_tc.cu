@@ -58,11 +58,7 @@ struct TcLayout {
   static constexpr size_t dxb = tgb + (BIAS ? 128 * 16 * 2 : 0);          // [128][8] fp32: dL/d(pe_bias) coming out of b_net
   static constexpr bool alias_dx = DEPTH >= 2;                            // dL/d(features) reuses the dead H_last slot
   static constexpr size_t dx = dxb + (BIAS ? 128 * 8 * 4 : 0);            // [128][32] fp32, XOR-swizzled (BIAS: the dead tbh slot)
-  // SPLIT (density-only instantiations): the backward steps commit their dgrad AHEAD of their wgrad, so the masked gradient
-  // dZ_l cannot overwrite H_l in place (the wgrad still reads it): it goes to `tz` or to the dead top hidden tile, alternating
-  static constexpr bool split = !SIGMA && NG == 2;  // (three groups leave no shared memory for the extra tile)
-  static constexpr size_t tz = dx + ((alias_dx || BIAS) ? 0 : 128 * 32 * 4);  // [128][64] dZ (fp16); for even DEPTH it later holds dL/d(features)
-  static constexpr size_t g_bytes = tz + (split ? 128 * 64 * 2 : 0);
+  static constexpr size_t g_bytes = dx + ((alias_dx || BIAS) ? 0 : 128 * 32 * 4);
   // ---- CTA-level fp32 scratch, indexed by CTA row (group * 128 + row) ----
   static constexpr size_t b_groups = (w_end + 127) / 128 * 128;
   static constexpr size_t b_scr = b_groups + NG * g_bytes;
@@ -70,8 +66,8 @@ struct TcLayout {
   static constexpr size_t fz0 = 0, flv = nrow, frho = 2 * nrow, fxw = 3 * nrow, fred = 6 * nrow, flb = fred + 16 * 16;  // floats
   static constexpr size_t fend = flb + (BIAS ? nrow : 0);
   static constexpr size_t b_lt = b_scr + fend * 4;
-  static constexpr size_t b_sync = (b_lt + sizeof(LevelTable) + 15) / 16 * 16;  // mbar[4] @0, tmem slot @32, grp_ran[4] @40, table mbarrier @56, mbar2[4] @64
-  static constexpr size_t bytes = (b_sync + 96 + 127) / 128 * 128;
+  static constexpr size_t b_sync = (b_lt + sizeof(LevelTable) + 15) / 16 * 16;  // mbar[4] @0, tmem slot @32, grp_ran[4] @40, table mbarrier @56
+  static constexpr size_t bytes = (b_sync + 64 + 127) / 128 * 128;
   // [bytes, bytes + staged table bytes): shared-memory copy of the coarsest levels of the fp16 hash table (FusedArgs::smem_levels)
   // ---- TMEM columns ----
   static constexpr uint32_t c_d = 0;                                      // group g: [64 g, 64 g + 64)
@@ -127,30 +123,6 @@ __device__ __forceinline__ void epi_mask_store(uint32_t taddr, unsigned char* ti
       pv[q] = *reinterpret_cast<const uint32_t*>(&o);
     }
     *p = v;
-  }
-}
-
-// out of place: dA = D masked by (activation tile `act` > 0), rounded to fp16, written to tile `dst`
-__device__ __forceinline__ void epi_mask_store_to(uint32_t taddr, const unsigned char* act, unsigned char* dst, int row, int c0) {
-  uint32_t r[32];
-  umma::tmem_ld32(taddr, r);
-  umma::tmem_ld_wait();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t off = umma::tile_off(row, c0 + 8 * i, 64);
-    const uint4 hv = *reinterpret_cast<const uint4*>(act + off);
-    const uint32_t* ph = reinterpret_cast<const uint32_t*>(&hv);
-    uint4 v;
-    uint32_t* pv = reinterpret_cast<uint32_t*>(&v);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&ph[q]));
-      const float d0 = h.x > 0.f ? __uint_as_float(r[8 * i + 2 * q]) : 0.f;
-      const float d1 = h.y > 0.f ? __uint_as_float(r[8 * i + 2 * q + 1]) : 0.f;
-      const __half2 o = __floats2half2_rn(d0, d1);
-      pv[q] = *reinterpret_cast<const uint32_t*>(&o);
-    }
-    *reinterpret_cast<uint4*>(dst + off) = v;
   }
 }
 
@@ -212,7 +184,6 @@ __global__ void __launch_bounds__(256 * NG, 1) inr_train_tc_kernel(const __grid_
     if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
       for (int g = 0; g < NG; ++g) umma::mbar_init(reinterpret_cast<uint64_t*>(smem + L::b_sync) + g, 1);
-      for (int g = 0; g < NG; ++g) umma::mbar_init(reinterpret_cast<uint64_t*>(smem + L::b_sync + 64) + g, 1);
       umma::mbar_init(tbar, 1);
       umma::mbar_fence_init();
       for (int g = 0; g < 4; ++g) grp_ran[g] = 0;
@@ -247,8 +218,6 @@ __global__ void __launch_bounds__(256 * NG, 1) inr_train_tc_kernel(const __grid_
   const uint32_t tlane = (uint32_t)(32 * q4) << 16;                  // epilogue lane quarter
   const bool issuer = (gw == 0 && lane == 0);
   uint32_t ph = 0;                                                   // mbarrier phase parity
-  uint64_t* mbar2 = reinterpret_cast<uint64_t*>(smem + L::b_sync + 64) + grp;  // SPLIT: "every wgrad of the tile has completed"
-  uint32_t ph2 = 0;
   uint32_t acc_on = NG == 3 ? 1u : 0u;                               // NG = 2: 0 on the group's first tile (wgrad MMAs overwrite)
   if (NG == 3) {  // the shared accumulators start from zero: every warp clears the columns of its own lane quarter
     const uint32_t tq0 = tm + ((uint32_t)(32 * (warp & 3)) << 16);
@@ -635,91 +604,43 @@ __global__ void __launch_bounds__(256 * NG, 1) inr_train_tc_kernel(const __grid_
       }
       publish();
     }
-    if (!L::split) {
-      {
-        const uint32_t s_hl = s_th + (DEPTH - 1) * 128 * 64 * 2;
-        if (issuer) {
-          umma::fence_after_sync();
-          mma_wgrad(L::c_wo, s_hl, s_tg, RG16, 16);          // dWo^T += H_last^T G
-          mma_dgrad(s_tg, RG16, s_wo, RG64, 16, 64);          // dH_last = G Wo
-          umma::commit(mbar);
-        }
-        wait_mma();
-        epi_mask_store(td + tlane + 32 * half, gt + L::th + (size_t)(DEPTH - 1) * 128 * 64 * 2, erow, 32 * half);
-        publish();
-      }
-#pragma unroll
-      for (int l = DEPTH - 1; l >= 1; --l) {
-        const uint32_t s_dz = s_th + l * 128 * 64 * 2, s_hp = s_th + (l - 1) * 128 * 64 * 2;
-        if (issuer) {
-          umma::fence_after_sync();
-          mma_wgrad(L::c_wh + 64 * (l - 1), s_dz, s_hp, RG64, 64);          // dWh_{l-1} += dZ_l^T H_{l-1}
-          mma_dgrad(s_dz, RG64, s_wh + (l - 1) * 64 * 64 * 2, RG64, 64, 64);  // dH_{l-1} = dZ_l Wh_{l-1}
-          umma::commit(mbar);
-        }
-        wait_mma();
-        epi_mask_store(td + tlane + 32 * half, gt + L::th + (size_t)(l - 1) * 128 * 64 * 2, erow, 32 * half);
-        publish();
-      }
+    {
+      const uint32_t s_hl = s_th + (DEPTH - 1) * 128 * 64 * 2;
       if (issuer) {
         umma::fence_after_sync();
-        mma_wgrad(L::c_w0, s_th, s_tx, RG32, 32);            // dW0 += dZ_0^T X
-        mma_dgrad(s_th, RG64, s_w0, RG32, 64, 32);           // dX = dZ_0 W0
+        mma_wgrad(L::c_wo, s_hl, s_tg, RG16, 16);          // dWo^T += H_last^T G
+        mma_dgrad(s_tg, RG16, s_wo, RG64, 16, 64);          // dH_last = G Wo
         umma::commit(mbar);
       }
       wait_mma();
-    } else {
-      // SPLIT: per step the dgrad (1-4 MMAs, what the epilogue waits for) is issued and committed FIRST, the wgrad (8 MMAs
-      // in one accumulate chain) behind it; the tensor pipe executes in order, so a step's wgrad has completed whenever a LATER
-      // commit has, and its operands may be reused from then on.  A tile's 59 small MMAs pay the pipe's per-instruction latency
-      // one after the other: this takes 32 of them off the path the 256 threads of the group wait on.
-      // hidden layer j (1..DEPTH): activation H_j in th[j-1]; its masked gradient dZ_j goes to zt(j): tz for (DEPTH - j) even,
-      // the dead top tile th[DEPTH-1] otherwise (H_DEPTH was last read by the top step's wgrad)
-      auto zt = [&](int j) -> size_t { return ((DEPTH - j) & 1) ? L::th + (size_t)(DEPTH - 1) * 128 * 64 * 2 : L::tz; };
-      {
-        const uint32_t s_hl = s_th + (DEPTH - 1) * 128 * 64 * 2;
-        if (issuer) {
-          umma::fence_after_sync();
-          mma_dgrad(s_tg, RG16, s_wo, RG64, 16, 64);          // dH_DEPTH = G Wo
-          umma::commit(mbar);
-          mma_wgrad(L::c_wo, s_hl, s_tg, RG16, 16);          // dWo^T += H_DEPTH^T G
-        }
-        wait_mma();
-        epi_mask_store_to(td + tlane + 32 * half, gt + L::th + (size_t)(DEPTH - 1) * 128 * 64 * 2, gt + zt(DEPTH), erow, 32 * half);
-        publish();
-      }
-#pragma unroll
-      for (int j = DEPTH - 1; j >= 1; --j) {  // consumes dZ_{j+1}, produces dZ_j
-        const uint32_t s_dz = umma::saddr(gt + zt(j + 1)), s_hj = s_th + (j - 1) * 128 * 64 * 2;
-        if (issuer) {
-          umma::fence_after_sync();
-          mma_dgrad(s_dz, RG64, s_wh + (j - 1) * 64 * 64 * 2, RG64, 64, 64);  // dH_j = dZ_{j+1} Wh_j
-          umma::commit(mbar);
-          mma_wgrad(L::c_wh + 64 * (j - 1), s_dz, s_hj, RG64, 64);          // dWh_j += dZ_{j+1}^T H_j
-        }
-        wait_mma();
-        epi_mask_store_to(td + tlane + 32 * half, gt + L::th + (size_t)(j - 1) * 128 * 64 * 2, gt + zt(j), erow, 32 * half);
-        publish();
-      }
-      {
-        const uint32_t s_dz = umma::saddr(gt + zt(1));
-        if (issuer) {
-          umma::fence_after_sync();
-          mma_dgrad(s_dz, RG64, s_w0, RG32, 64, 32);           // dX = dZ_1 W0
-          umma::commit(mbar);
-          mma_wgrad(L::c_w0, s_dz, s_tx, RG32, 32);            // dW0 += dZ_1^T X
-          umma::commit(mbar2);                                 // ... after which every operand tile of this tile is free
-        }
-        wait_mma();
-      }
+      epi_mask_store(td + tlane + 32 * half, gt + L::th + (size_t)(DEPTH - 1) * 128 * 64 * 2, erow, 32 * half);
+      publish();
     }
+#pragma unroll
+    for (int l = DEPTH - 1; l >= 1; --l) {
+      const uint32_t s_dz = s_th + l * 128 * 64 * 2, s_hp = s_th + (l - 1) * 128 * 64 * 2;
+      if (issuer) {
+        umma::fence_after_sync();
+        mma_wgrad(L::c_wh + 64 * (l - 1), s_dz, s_hp, RG64, 64);          // dWh_{l-1} += dZ_l^T H_{l-1}
+        mma_dgrad(s_dz, RG64, s_wh + (l - 1) * 64 * 64 * 2, RG64, 64, 64);  // dH_{l-1} = dZ_l Wh_{l-1}
+        umma::commit(mbar);
+      }
+      wait_mma();
+      epi_mask_store(td + tlane + 32 * half, gt + L::th + (size_t)(l - 1) * 128 * 64 * 2, erow, 32 * half);
+      publish();
+    }
+    if (issuer) {
+      umma::fence_after_sync();
+      mma_wgrad(L::c_w0, s_th, s_tx, RG32, 32);            // dW0 += dZ_0^T X
+      mma_dgrad(s_th, RG64, s_w0, RG32, 64, 32);           // dX = dZ_0 W0
+      umma::commit(mbar);
+    }
+    wait_mma();
     }
     acc_on = 1u;
     // dL/d(features): fp32 [128][32], feature pair (2l, 2l+1) of row r at r*32 + ((2l) ^ ((r & 15) << 1)) -- 8-byte
     // accesses, conflict-free for both the row-per-lane epilogue writes and the sample-pair reads of the scatter
-    // SPLIT: the last wgrad still reads dZ_1 -- dL/d(features) takes the OTHER dead 16 KB tile (odd DEPTH >= 3: the top hidden
-    // tile, even DEPTH: tz; DEPTH 1 keeps its own slot)
-    float* sdx = reinterpret_cast<float*>(gt + (BIAS ? L::tbh : (L::alias_dx ? ((L::split && !(DEPTH & 1)) ? L::tz : L::th + (size_t)(DEPTH - 1) * 128 * 64 * 2) : L::dx)));
+    float* sdx = reinterpret_cast<float*>(gt + (BIAS ? L::tbh : (L::alias_dx ? L::th + (size_t)(DEPTH - 1) * 128 * 64 * 2 : L::dx)));
     if (!(a.ablate & 4u)) {
       uint32_t d[16];
       umma::tmem_ld16(td + tlane + 16 * half, d);
@@ -771,10 +692,6 @@ __global__ void __launch_bounds__(256 * NG, 1) inr_train_tc_kernel(const __grid_
       scatter_warp<false>(xn, lt, cfg.grid.n_levels, a.table, fetch, inv_gscale, a.g_table, gx, slow);
     }
     tick(5);
-    if (L::split && !(a.ablate & 4u)) {  // every wgrad of this tile has read its operands (long done: the scatter ran meanwhile)
-      umma::mbar_wait(mbar2, ph2);
-      ph2 ^= 1u;
-    }
     group_barrier(grp, kGT);  // the group's tiles (incl. the aliased dX slot) are free for the next tile
   }
   if (TIMED) {
