@@ -135,13 +135,15 @@ def cpu_oracle_throughput(n_pixels=8192, n_samples=128, steps=2, warmup=1, threa
         return time.perf_counter() - t0
 
     small = n_pixels
-    t_probe = step(256)  # untimed: thread pool / allocator warm-up
-    if budget_s is not None:  # full-size iterations cost ~n_pixels / 256 / 2.5 probes (large batches run more efficiently)
-        est_full = max(t_probe * n_pixels / 256 / 2.5, 1e-3)
-        if (warmup + steps) * est_full > budget_s:
-            per_step = max(budget_s - est_full, 0.25 * budget_s) / max(warmup + steps - 1, 1)
-            small = int(max(256, min(n_pixels, 256 * per_step / t_probe)) // 256 * 256)
-    for _ in range(warmup):
+    step(256)  # untimed: thread pool / allocator warm-up
+    n_warm = warmup
+    if budget_s is not None:  # ONE full-size warm-up iteration is the yardstick: do warmup + steps of them fit in the budget?
+        t_full = step(n_pixels)
+        n_warm = max(warmup - 1, 0)
+        if (n_warm + steps) * t_full > budget_s - t_full:
+            per_step = max(budget_s - 2 * t_full, 0.25 * budget_s) / max(n_warm + steps - 1, 1)
+            small = int(max(256, min(n_pixels, n_pixels * per_step / t_full * 0.5)) // 256 * 256)  # small batches run less efficiently
+    for _ in range(n_warm):
         step(small)
     sizes = [n_pixels] + [small] * (steps - 1)
     times = [step(n) for n in sizes]

@@ -114,12 +114,41 @@ def config2_through_cli(cli, compat, nb, dev, tmp, n_iter=600):
     argv = ["nesvor", "reconstruct", "--input-slices", folder, "--output-model", os.path.join(tmp, "model_cfg2.pt"), "--n-iter", str(n_iter),
             "--batch-size", "8192", "--n-samples", "128", "--depth", "3", "--finest-resolution", "%.6f" % finest, "--no-pixel-variance",
             "--no-slice-variance", "--no-transformation-optimization", "--verbose", "0", "--seed", "0"]
+    # wall time of the command's phases: the names `nesvor.cli.commands` calls (cli/commands.py:100-125) wrapped with timers
+    import time as _time
+
+    import nesvor.cli.commands as cmds
+
+    phases = {}
+
+    def timed(name, fn):
+        def call(*a_, **k_):
+            torch.cuda.synchronize()
+            t0 = _time.perf_counter()
+            try:
+                return fn(*a_, **k_)
+            finally:
+                torch.cuda.synchronize()
+                phases[name] = phases.get(name, 0.0) + _time.perf_counter() - t0
+
+        return call
+
+    saved = {n: getattr(cmds, n) for n in ("inputs", "train", "sample_volume", "sample_slices", "outputs")}
+    for n, fn in saved.items():
+        setattr(cmds, n, timed(n, fn))
     old_argv, sys.argv = sys.argv, argv
+    torch.cuda.synchronize()
+    t_cmd = _time.perf_counter()
     try:
         cli.main()
     finally:
         sys.argv = old_argv
+        for n, fn in saved.items():
+            setattr(cmds, n, fn)
+    torch.cuda.synchronize()
     info = dict(compat.LAST_TRAIN_INFO)
+    info["command_wall_s"] = _time.perf_counter() - t_cmd
+    info["phase_wall_s"] = phases
     info["argv"] = argv[1:]
     if "ms_per_iteration" in info:
         info["queries_per_s"] = info["queries_per_iteration"] / info["ms_per_iteration"] * 1e3
