@@ -265,9 +265,15 @@ __global__ void __launch_bounds__(256 * NG, 1) inr_train_tc_kernel(const __grid_
     group_barrier(grp, kGT);
     tick(1);
   };
+  // The group's 8 warps used to poll the mbarrier each (try_wait wakes every few dozen cycles): 36 M of the kernel's 298 M
+  // warp instructions were polling, issued from the same schedulers the other group's gather / scatter code needs
+  // (profiles/r02_kernelA_tcgen05_ncu_summary.txt).  Now ONE warp polls and releases the others through the group's named
+  // barrier, where waiting costs no issue slots.  a.ablate bit 3 (profiling) restores the old scheme.
+  const bool poll_all = (a.ablate & 8u) != 0;
   auto wait_mma = [&]() {
-    umma::mbar_wait(mbar, ph);
+    if (poll_all || gw == 0) umma::mbar_wait(mbar, ph);
     ph ^= 1u;
+    if (!poll_all) group_barrier(grp, kGT);
     umma::fence_after_sync();
     tick(2);
   };
