@@ -296,11 +296,13 @@ int nsv_adamw_step_dp(float* param, const void* const* peer_grads, float* exp_av
  * `stream`) to every rank and waits for all announcements before pulling gradients; epilogue: the rank's last block announces
  * "all my reads and my writes into your copies are done" and waits for the same from every rank, so that when the kernel
  * completes the local fp16 / fp32 copies are whole and the local gradient may be cleared.  A wait gives up after a few
- * seconds (a dead rank must not hang the others' GPUs) and records the epoch in flag word 33. */
+ * seconds (a dead rank must not hang the others' GPUs) and records the epoch in flag word 33.
+ * sync_mode: 1 = only the rendezvous BEFORE (the caller still synchronises the ranks after the kernel), 2 = only the one AFTER,
+ * 3 = both. */
 int nsv_adamw_step_dp_sync(float* param, const void* const* peer_grads, float* exp_avg, float* exp_avg_sq,
                            void* const* peer_param_f16, int world, int rank, int64_t n, float lr, float beta1, float beta2,
                            float eps, float weight_decay, int step, float grad_unscale, int64_t f32_lo,
-                           void* const* peer_param_f32, void* const* peer_flags, uint64_t epoch, void* stream);
+                           void* const* peer_param_f32, void* const* peer_flags, uint64_t epoch, int sync_mode, void* stream);
 
 
 /* tcgen05 / TMEM bring-up check used by tests/test_gpu_umma.py: runs every tensor-core operand

@@ -105,10 +105,11 @@ template <int WORLD>
 __global__ void __launch_bounds__(256) adamw_dp_kernel(float* __restrict__ p, const __grid_constant__ PeerPtrs peers, float* __restrict__ m,
                                                        float* __restrict__ v, int world_rt, int64_t lo, int64_t hi, int64_t f32_lo, float lr,
                                                        float b1, float b2, float eps, float wd, float step_size, float inv_sqrt_bc2,
-                                                       float unscale, int rank, unsigned long long epoch) {
+                                                       float unscale, int rank, unsigned long long epoch, int sync_mode) {
   const int world = WORLD > 0 ? WORLD : world_rt;
-  const bool rendezvous = peers.flags[0] != nullptr;
-  if (rendezvous) {
+  // sync_mode bit 0: rendezvous before the gradients are pulled; bit 1: rendezvous after the copies are written
+  const bool rendezvous = peers.flags[0] != nullptr && (sync_mode & 2);
+  if (peers.flags[0] != nullptr && (sync_mode & 1)) {
     // (1) this rank's gradient is complete (kernel A precedes this launch on the stream): tell every rank; then every block
     // waits until every rank has said so before it pulls gradients through the peer pointers
     if (threadIdx.x == 0) {
@@ -212,7 +213,7 @@ extern "C" int nsv_adamw_shard_bounds(int64_t n, int world, int rank, int64_t* l
 static int adamw_step_dp_impl(float* param, const void* const* peer_grads, float* exp_avg, float* exp_avg_sq,
                              void* const* peer_param_f16, int world, int rank, int64_t n, float lr, float beta1, float beta2,
                              float eps, float weight_decay, int step, float grad_unscale, int64_t f32_lo,
-                             void* const* peer_param_f32, void* const* peer_flags, uint64_t epoch, void* stream) {
+                             void* const* peer_param_f32, void* const* peer_flags, uint64_t epoch, int sync_mode, void* stream) {
   using namespace nsv;
   NSV_REQUIRE(n >= 0 && step >= 1, "nsv_adamw_step_dp: bad n / step");
   NSV_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "nsv_adamw_step_dp: world must be 1..16, rank in [0, world)");
@@ -238,7 +239,7 @@ static int adamw_step_dp_impl(float* param, const void* const* peer_grads, float
   const int grid = (int)(blocks < (int64_t)num_sms() * 8 ? blocks : (int64_t)num_sms() * 8);
 #define NSV_DP_LAUNCH(W)                                                                                                            \
   adamw_dp_kernel<W><<<grid, 256, 0, (cudaStream_t)stream>>>(param, pp, exp_avg, exp_avg_sq, world, lo, hi, f32_lo, lr, beta1, beta2, eps, weight_decay, \
-                                                             step_size, inv_sqrt_bc2, grad_unscale, rank, (unsigned long long)epoch)
+                                                             step_size, inv_sqrt_bc2, grad_unscale, rank, (unsigned long long)epoch, sync_mode)
   if (world == 2) NSV_DP_LAUNCH(2);
   else if (world == 4) NSV_DP_LAUNCH(4);
   else if (world == 8) NSV_DP_LAUNCH(8);
@@ -252,17 +253,18 @@ extern "C" int nsv_adamw_step_dp(float* param, const void* const* peer_grads, fl
                                  float eps, float weight_decay, int step, float grad_unscale, int64_t f32_lo,
                                  void* const* peer_param_f32, void* stream) {
   return adamw_step_dp_impl(param, peer_grads, exp_avg, exp_avg_sq, peer_param_f16, world, rank, n, lr, beta1, beta2, eps, weight_decay,
-                            step, grad_unscale, f32_lo, peer_param_f32, nullptr, 0, stream);
+                            step, grad_unscale, f32_lo, peer_param_f32, nullptr, 0, 0, stream);
 }
 
 extern "C" int nsv_adamw_step_dp_sync(float* param, const void* const* peer_grads, float* exp_avg, float* exp_avg_sq,
                                       void* const* peer_param_f16, int world, int rank, int64_t n, float lr, float beta1, float beta2,
                                       float eps, float weight_decay, int step, float grad_unscale, int64_t f32_lo,
-                                      void* const* peer_param_f32, void* const* peer_flags, uint64_t epoch, void* stream) {
+                                      void* const* peer_param_f32, void* const* peer_flags, uint64_t epoch, int sync_mode, void* stream) {
   using namespace nsv;
   NSV_REQUIRE(peer_flags && epoch > 0, "nsv_adamw_step_dp_sync: needs the ranks' flag blocks and a positive, strictly increasing epoch");
+  NSV_REQUIRE(sync_mode >= 1 && sync_mode <= 3, "nsv_adamw_step_dp_sync: sync_mode is 1 (rendezvous before), 2 (after) or 3 (both)");
   return adamw_step_dp_impl(param, peer_grads, exp_avg, exp_avg_sq, peer_param_f16, world, rank, n, lr, beta1, beta2, eps, weight_decay,
-                            step, grad_unscale, f32_lo, peer_param_f32, peer_flags, epoch, stream);
+                            step, grad_unscale, f32_lo, peer_param_f32, peer_flags, epoch, sync_mode, stream);
 }
 
 extern "C" int nsv_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* param_f16, int64_t n, float lr,

@@ -460,16 +460,21 @@ class FusedTrainer:
             # step, profiles/r02_bench_8gpu_weak*.json -- every block of the in-kernel variant pays a system-scope fence for
             # its peer writes); "kernel": the ranks' rendezvous inside the kernel (nsv_adamw_step_dp_sync), equal at 2-4 ranks
             self.args.dp_sync = os.environ.get("NSV_DP_SYNC", "host")
-        if self.dp_mode == "peer" and self.args.dp_sync == "kernel":
-            # ONE launch: rendezvous of the ranks (flags in peer memory), reduce-scatter, AdamW, all-gather, rendezvous
+        if self.dp_mode == "peer" and self.args.dp_sync in ("kernel", "hybrid"):
+            # "kernel": ONE launch -- rendezvous of the ranks (flags in peer memory), reduce-scatter, AdamW, all-gather, rendezvous.
+            # "hybrid": the rendezvous BEFORE inside the kernel (flags only: kernel A has completed, nothing to fence), the one
+            # AFTER as a host-launched symmetric-memory barrier (the in-kernel one costs every block a system-scope fence).
+            mode = 3 if self.args.dp_sync == "kernel" else 1
             with torch.cuda.device(st.device):
                 rc = _lib.lib().nsv_adamw_step_dp_sync(
                     _lib.ptr(st.flat), st.peer_grads, _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), st.peer_flat16,
                     ctypes.c_int(world), ctypes.c_int(rank), ctypes.c_int64(st.n_train), ctypes.c_float(self.lr), ctypes.c_float(0.9),
                     ctypes.c_float(0.99), ctypes.c_float(1e-15), ctypes.c_float(1e-2), ctypes.c_int(self.iteration),
                     ctypes.c_float(1.0 / world), ctypes.c_int64(st.tail_lo), st.peer_tail32, st.peer_flags,
-                    ctypes.c_uint64(self.iteration), _lib.stream(st.device))
+                    ctypes.c_uint64(self.iteration), ctypes.c_int(mode), _lib.stream(st.device))
             _lib.check(rc, "nsv_adamw_step_dp_sync")
+            if mode == 1:
+                st.peer_handle.barrier()  # every owner has read this rank's gradient and written this rank's copies
             st.grad[: st.n_train].zero_()
             return
         if self.dp_mode == "peer":

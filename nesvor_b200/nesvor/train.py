@@ -76,7 +76,7 @@ class Dataset(object):
             idx = torch.randperm(self.xyz.shape[0], device=device)
             if self.dist is not None:
                 self.dist.broadcast(idx, src=0)
-            if self.locality_batch:
+            if getattr(self, "locality_batch", 0):
                 idx = self._order_inside_batches(idx, self.locality_batch)
             self.xyz, self.v, self.slice_idx = self.xyz[idx], self.v[idx], self.slice_idx[idx]
         sl = slice(self.count, self.count + batch_size)

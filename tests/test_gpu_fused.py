@@ -108,6 +108,10 @@ CONFIGS = {
 }
 
 
+# relative-L2 bounds of the fused kernels' gradients against the fp32 oracle (fp16 backward operands with a power-of-two loss scale)
+GRAD_TOL = dict(table=2e-2, density_net=2e-2, logit_coef=2e-2, log_var_slice=2e-2, sigma_net=2e-2, slice_embedding=2e-2, b_net=2e-2, axisangle=3e-2)
+
+
 @pytest.fixture
 def fused_impl(request):
     """"tcgen05x3" = the tcgen05 all-phases kernel with three 128-sample groups per CTA (768 threads, shared TMEM weight-gradient
@@ -149,30 +153,35 @@ def test_fused_train_step_parity(native_lib, name, fused_impl):
     for k in ("MSE", "logVar", "imageReg", "biasReg"):
         if k in losses_o:
             np.testing.assert_allclose(float(got[k]), float(losses_o[k]), rtol=2e-3, atol=1e-6, err_msg=k)
-    # gradients (fp16 backward operands): table, MLP weights, per-slice parameters
-    assert rel_l2(st.seg("table", st.grad).cpu(), om.P["table"].grad) < 2e-2
+    # gradients (fp16 backward operands): table, MLP weights, per-slice parameters.  Every error is printed (pytest -s / the
+    # captured output of a failure) next to its bound; the bounds are ~2x the largest value measured on B200 over all
+    # configurations and implementations (profiles/r02_gradient_errors.txt)
+    errs = {"table": rel_l2(st.seg("table", st.grad).cpu(), om.P["table"].grad)}
     gd = st.seg("mlp", st.grad).cpu()
     ws = [om.P[f"density_net.w{i}"].grad.reshape(-1) for i in range(args.depth + 1)]
     nd = sum(w.numel() for w in ws)
-    assert rel_l2(gd[st.off_density : st.off_density + nd], torch.cat(ws)) < 2e-2
+    errs["density_net"] = rel_l2(gd[st.off_density : st.off_density + nd], torch.cat(ws))
     if not args.no_slice_scale:
-        assert rel_l2(st.seg("logit_coef", st.grad).cpu(), om.P["logit_coef"].grad) < 2e-2
+        errs["logit_coef"] = rel_l2(st.seg("logit_coef", st.grad).cpu(), om.P["logit_coef"].grad)
     if not args.no_slice_variance:
-        assert rel_l2(st.seg("log_var_slice", st.grad).cpu(), om.P["log_var_slice"].grad) < 2e-2
+        errs["log_var_slice"] = rel_l2(st.seg("log_var_slice", st.grad).cpu(), om.P["log_var_slice"].grad)
     if not args.no_pixel_variance:
         from nesvor_b200.nesvor.fused import _unpack_sigma
 
         n = model.sigma_net.params.numel()
         gs = _unpack_sigma(gd[st.off_sigma : st.off_sigma + n], args.width)
         ws = torch.cat([om.P[f"sigma_net.w{i}"].grad.reshape(-1) for i in range(args.depth + 1)])
-        assert rel_l2(gs, ws) < 2e-2
-        assert rel_l2(st.seg("slice_embedding", st.grad).cpu(), om.P["slice_embedding"].grad.reshape(-1)) < 2e-2
+        errs["sigma_net"] = rel_l2(gs, ws)
+        errs["slice_embedding"] = rel_l2(st.seg("slice_embedding", st.grad).cpu(), om.P["slice_embedding"].grad.reshape(-1))
     if args.n_levels_bias:
         n = model.b_net.params.numel()
         wb = torch.cat([om.P[f"b_net.w{i}"].grad.reshape(-1) for i in range(args.depth + 1)])
-        assert rel_l2(gd[st.off_bias : st.off_bias + n], wb) < 2e-2
+        errs["b_net"] = rel_l2(gd[st.off_bias : st.off_bias + n], wb)
     if not args.no_transformation_optimization:
-        assert rel_l2(st.seg("axisangle", st.grad).cpu(), om.P["axisangle"].grad.reshape(-1)) < 3e-2
+        errs["axisangle"] = rel_l2(st.seg("axisangle", st.grad).cpu(), om.P["axisangle"].grad.reshape(-1))
+    print(f"GRADERR {name} [{fused_impl}] " + " ".join(f"{k}={v:.3e}" for k, v in errs.items()))
+    for k, v in errs.items():
+        assert v < GRAD_TOL[k], (k, v, GRAD_TOL[k])
 
 
 @pytest.mark.parametrize("single_precision", [True, False])

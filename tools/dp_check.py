@@ -38,16 +38,16 @@ def main():
     trainers = {}
     # "peer": the fused kernel with the ranks' rendezvous inside it (nsv_adamw_step_dp_sync, the default);
     # "peer_host": the same kernel bracketed by two host-launched symmetric-memory barriers (nsv_adamw_step_dp)
-    for mode in ("peer", "peer_host", "allreduce"):
+    for mode in ("peer", "peer_host", "peer_hybrid", "allreduce"):
         torch.manual_seed(7)  # identical initial parameters on every rank and for all trainers
         model = nb.NeSVoR(dataset.transformation, dataset.resolution, dataset.mean, dataset.bounding_box, args)
         a = copy.copy(args)
-        a.dp_optimizer = "peer" if mode == "peer_host" else mode
-        a.dp_sync = "host" if mode == "peer_host" else "kernel"  # both synchronisation schemes are exercised whatever the default is
+        a.dp_optimizer = "peer" if mode.startswith("peer") else mode
+        a.dp_sync = {"peer_host": "host", "peer_hybrid": "hybrid"}.get(mode, "kernel")  # every synchronisation scheme is exercised whatever the default is
         trainers[mode] = FusedTrainer(model, a)
     g = torch.Generator().manual_seed(100 + rank)
     P = dataset.xyz.shape[0]
-    tp, th, ta = trainers["peer"], trainers["peer_host"], trainers["allreduce"]
+    tp, th, ty, ta = trainers["peer"], trainers["peer_host"], trainers["peer_hybrid"], trainers["allreduce"]
     for name in ("slice_embedding", "logit_coef", "log_var_slice", "axisangle"):
         t = tp.state.seg(name)
         if t is not None:
@@ -58,23 +58,25 @@ def main():
         batch = dict(xyz=dataset.xyz[sel], v=dataset.v[sel], slice_idx=dataset.slice_idx[sel])
         # kernel A accumulates with float atomics (run-to-run round-off that Adam's normalisation amplifies), so the two
         # optimiser paths are compared on the SAME per-rank gradient: one forward / backward, copied into both trainers
-        for tr in (tp, th, ta):
+        for tr in (tp, th, ty, ta):
             tr.iteration += 1
             tr.state.losses.zero_()
         ta.state.forward_backward(batch["xyz"], batch["v"], batch["slice_idx"], noise)
         if it == 0:
             tp._setup_dp(dist, world)
             th._setup_dp(dist, world)
-        tp.state.grad[: tp.state.n_total].copy_(ta.state.grad[: ta.state.n_total])
-        th.state.grad[: th.state.n_total].copy_(ta.state.grad[: ta.state.n_total])
-        for tr in (tp, th, ta):
+            ty._setup_dp(dist, world)
+        for tr in (tp, th, ty):
+            tr.state.grad[: tr.state.n_total].copy_(ta.state.grad[: ta.state.n_total])
+        for tr in (tp, th, ty, ta):
             tr._dp_update(dist, world)
         # the next forward must see the same parameters in both trainers (checked at the end); keep them in lockstep
     torch.cuda.synchronize()
     assert tp.dp_mode == "peer" and ta.dp_mode == "allreduce", (tp.dp_mode, ta.dp_mode)
     n = tp.state.n_train
     assert th.dp_mode == "peer"
-    d_host = (th.state.flat16[:n].float() - tp.state.flat16[:n].float()).abs().max().item()  # the two synchronisation schemes: same kernel, same bits
+    d_host = max((th.state.flat16[:n].float() - tp.state.flat16[:n].float()).abs().max().item(),
+                 (ty.state.flat16[:n].float() - tp.state.flat16[:n].float()).abs().max().item())  # the three synchronisation schemes: same kernel, same bits
     d16 = (tp.state.flat16[:n].float() - ta.state.flat16[:n].float()).abs().max().item()
     changed = (tp.state.flat16[:n] != 0).float().mean().item()
     # the per-slice parameters kernel A reads in fp32 (slice embedding, slice scale / variance, poses) must be current on

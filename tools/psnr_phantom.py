@@ -51,6 +51,10 @@ CFGS = {
     # joint pose + INR optimisation (models.py:275-278,357-363, train.py:224)
     "3p": dict(sim=dict(n=64, n_stacks=6, res_r=1.0, res_s=1.0, gap=3.0, motion_deg=3.0, motion_mm=1.5),
                args=dict(no_transformation_optimization=False)),
+    # BASELINE config 3 in full: 256^3 phantom, 6 stacks with injected motion, reference-default heads, pose optimisation on,
+    # n-samples 256, batch 4096, 8000 iterations (--pose --iters 8000 --batch 4096 --samples 256)
+    "3": dict(sim=dict(n=256, n_stacks=6, res_r=1.0, res_s=1.0, gap=3.0, motion_deg=3.0, motion_mm=1.5),
+              args=dict(no_transformation_optimization=False)),
     # BASELINE config 2 in full (128^3, 16 levels, 64 x 3 hidden, B = 8192, S = 128, 5000 iterations): --ours-only
     "2": dict(sim=dict(n=128, n_stacks=3, res_r=1.0, res_s=1.0, gap=3.0),
               args=dict(n_levels=16, depth=3, width=64, no_pixel_variance=True, no_slice_variance=True)),
