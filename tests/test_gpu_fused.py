@@ -109,7 +109,9 @@ CONFIGS = {
 
 
 # relative-L2 bounds of the fused kernels' gradients against the fp32 oracle (fp16 backward operands with a power-of-two loss scale)
-GRAD_TOL = dict(table=2e-2, density_net=2e-2, logit_coef=2e-2, log_var_slice=2e-2, sigma_net=2e-2, slice_embedding=2e-2, b_net=2e-2, axisangle=3e-2)
+# measured maxima on B200 over all configurations x implementations (round 2, profiles/r02_gradient_errors.txt):
+# table 6.5e-4, density_net 1.7e-4, logit_coef 4.7e-6, log_var_slice 4.3e-7, sigma_net 1.9e-5, slice_embedding 1.6e-4, b_net 1.0e-4, axisangle 1.3e-3
+GRAD_TOL = dict(table=2e-3, density_net=5e-4, logit_coef=2e-5, log_var_slice=5e-6, sigma_net=1e-4, slice_embedding=5e-4, b_net=5e-4, axisangle=4e-3)
 
 
 @pytest.fixture

@@ -123,7 +123,7 @@ def _world_matrix(ax: torch.Tensor) -> torch.Tensor:
     return M
 
 
-def pose_error(ax_est: torch.Tensor, ax_true: torch.Tensor) -> dict:
+def pose_error(ax_est: torch.Tensor, ax_true: torch.Tensor, weight: torch.Tensor = None) -> dict:
     """Per-slice pose error up to the global rigid gauge (a reconstruction in a rigidly moved frame is as good):
     G_i = M_est_i M_true_i^-1 maps the true world frame to the estimated one; the residual of G_i against the mean G is
     reported as a rotation angle (degrees) and as the displacement of the slice centre (mm), mean and max over slices."""
@@ -137,7 +137,13 @@ def pose_error(ax_est: torch.Tensor, ax_true: torch.Tensor) -> dict:
     disp = (moved - (centre @ Rm.T + tm)).norm(dim=1)
     Rres = Rm.T @ G[:, :3, :3]
     ang = torch.rad2deg(torch.acos(((Rres.diagonal(dim1=1, dim2=2).sum(1) - 1) / 2).clamp(-1, 1)))
-    return {"rot_deg_mean": float(ang.mean()), "rot_deg_max": float(ang.max()), "centre_mm_mean": float(disp.mean()), "centre_mm_max": float(disp.max())}
+    out = {"rot_deg_mean": float(ang.mean()), "rot_deg_median": float(ang.median()), "rot_deg_max": float(ang.max()),
+           "centre_mm_mean": float(disp.mean()), "centre_mm_median": float(disp.median()), "centre_mm_max": float(disp.max())}
+    if weight is not None:  # weighted by the number of pixels a slice contributes (slices through the phantom's caps carry little signal)
+        w = weight.double().cpu() / weight.double().sum().cpu()
+        out["rot_deg_pixel_weighted"] = float((ang * w).sum())
+        out["centre_mm_pixel_weighted"] = float((disp * w).sum())
+    return out
 
 
 def run_pose_recovery(cfg_name="3p", n_iter=3000, batch=4096, n_samples=64, device=None, log=print):
@@ -170,7 +176,8 @@ def run_pose_recovery(cfg_name="3p", n_iter=3000, batch=4096, n_samples=64, devi
         gt = volume[0, 0].reshape(-1).cpu()
         attach_render_state(inr, args)
         rec = torch.cat([fused_render(inr, grid[i : i + (1 << 18)].to(device), None, 0.0, 1).cpu() for i in range(0, grid.shape[0], 1 << 18)])
-        out[tag] = {"pose_error_before": pose_error(nominal, true_ax[keep]), "pose_error_after": pose_error(est, true_ax[keep]),
+        n_px = torch.tensor([float(s.mask.sum()) for s in slices])
+        out[tag] = {"pose_error_before": pose_error(nominal, true_ax[keep], n_px), "pose_error_after": pose_error(est, true_ax[keep], n_px),
                     "psnr_inside": psnr(rec, gt, gt > 0), "psnr_full": psnr(rec, gt), "train_wall_s": wall, "n_slices": len(slices)}
         log(tag, json.dumps(out[tag]))
     return out
