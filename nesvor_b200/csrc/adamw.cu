@@ -75,7 +75,8 @@ struct PeerPtrs {
   float* p32[kMaxPeers];  // optional fp32 mirror of the elements [f32_lo, n): the per-slice parameters kernel A reads in fp32
   // optional in-kernel rendezvous (replaces the two host-launched symmetric-memory barriers around the kernel):
   // flags[r] = rank r's flag block in peer memory, 64 x u64: [0,16) "gradient of rank i complete" (written by rank i),
-  // [16,32) "rank i has read every gradient and written every fp16 / fp32 copy", [32] block ticket counter, [33] time-out marker
+  // [16,32) "rank i has read every gradient and written every fp16 / fp32 copy", [32] block ticket counter, [33] time-out marker,
+  // [34] device-scope "every rank's gradient is complete" (written by block 0 of this rank)
   unsigned long long* flags[kMaxPeers];
 };
 
@@ -112,10 +113,24 @@ __global__ void __launch_bounds__(256) adamw_dp_kernel(float* __restrict__ p, co
   if (peers.flags[0] != nullptr && (sync_mode & 1)) {
     // (1) this rank's gradient is complete (kernel A precedes this launch on the stream): tell every rank; then every block
     // waits until every rank has said so before it pulls gradients through the peer pointers
+    // Only block 0 talks to the other ranks (system-scope loads of flags that peers write over NVLink cost microseconds each,
+    // and 1184 blocks x 8 flags of them made the first version slower than a host-launched barrier); it then publishes
+    // "everybody is ready" in a device-scope flag the other blocks of this rank wait on.
     if (threadIdx.x == 0) {
-      if (blockIdx.x == 0)
+      unsigned long long* mine = peers.flags[rank];
+      if (blockIdx.x == 0) {
         for (int r = 0; r < world; ++r) st_release_sys(peers.flags[r] + rank, epoch);
-      for (int r = 0; r < world; ++r) wait_flag(peers.flags[rank], r, epoch);
+        for (int r = 0; r < world; ++r) wait_flag(mine, r, epoch);
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(mine + 34), "l"(epoch) : "memory");
+      } else {
+        const long long t0 = clock64();
+        unsigned long long v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + 34) : "memory");
+          if (v >= epoch) break;
+          __nanosleep(32);
+        } while (clock64() - t0 < (9ll << 30));
+      }
     }
     __syncthreads();
   }
