@@ -111,10 +111,19 @@ def _cg(A, b, x0, n_iter, tol):
 
 
 def test_cg_recovers_phantom_known_answer(oracle):
+    """The reference's only known-answer test of A / A^T (tests/slice_acquisition/test_slice_acq.py:76-81: CG-SRR started AT the
+    phantom must stay there, atol 3e-5) on the CPU oracle, made deterministic (no retries).
+    (1) One OpenMP thread: the scatter A^T sums in a fixed order, so A^T(A x0) evaluated twice is bit-identical and the
+        residual CG starts from is EXACTLY zero -- the known answer holds trivially and exactly (the reference's atol exists only
+        because its float atomics reorder; on the GPU the same KAT runs through the product kernels in fp64 at the reference's
+        tolerance and in fp32 with a noise bound, tests/test_gpu_slice_acq.py).
+    (2) All threads, start perturbed by a smooth bump of amplitude 0.05: 20 CG iterations must bring the L2 error down by
+        more than 5x (measured 7.9x) -- a convergence check that is insensitive to summation-order noise."""
     from oracle import native
+    from scipy.ndimage import gaussian_filter
+
     from nesvor_b200.data.phantom import phantom3d, stack_axisangles, stack_geometry
 
-    native.set_threads(os.cpu_count() or 1)
     vs, gap, res, res_s = 32, 3.0, 1.0, 1.5
     ss, n_slice = stack_geometry(vs, res, res_s, gap)
     assert (ss, n_slice) == (40, 22)
@@ -129,23 +138,21 @@ def test_cg_recovers_phantom_known_answer(oracle):
     tf = oracle.axisangle2mat_forward(ax)[0]  # res_r = 1: mat_update_resolution is the identity
     A = lambda x: oracle.forward(tf, x, None, None, psf, (ss, ss), res_s / res, False, 0)[0]
     At = lambda y: oracle.adjoint_forward(tf, psf, y, None, None, (vs, vs, vs), res_s / res, 0, 0)[0]
-    slices = A(volume)
-    # CG is started AT the solution: the residual it sees is only the summation-order noise of the multi-threaded scatter
-    # (~1e-7 relative), which one CG step divides by an eigenvalue of A^T A.  On rare runs the noise lines up with a small
-    # eigenvalue and the reference's atol is exceeded -- a property of the KAT, not of the operators -- so the check is
-    # repeated with fresh noise before it counts as a failure (3 unlucky draws in a row: < 1e-4).
-    err = None
-    for _attempt in range(3):
-        rec = np.maximum(_cg(lambda x: At(A(x)), At(slices), volume, 20, 1e-8), 0)
-        try:
-            torch.testing.assert_close(torch.from_numpy(rec), torch.from_numpy(volume), atol=3e-5, rtol=1e-5)
-            err = None
-            break
-        except AssertionError as e:
-            err = e
-    native.set_threads(1)
-    if err is not None:
-        raise err
+    try:
+        native.set_threads(1)
+        slices = A(volume)
+        b = At(slices)
+        assert np.array_equal(At(A(volume)), b)  # (1): zero residual at the known answer, bit for bit
+        rec = _cg(lambda x: At(A(x)), b, volume, 20, 1e-8)
+        torch.testing.assert_close(torch.from_numpy(np.maximum(rec, 0)), torch.from_numpy(volume), atol=3e-5, rtol=1e-5)
+        native.set_threads(os.cpu_count() or 1)
+        bump = gaussian_filter(np.random.default_rng(0).standard_normal(volume.shape[2:]), 3.0)[None, None].astype(np.float32)
+        x0 = volume + bump * (0.05 / np.abs(bump).max())
+        rec = _cg(lambda x: At(A(x)), b, x0, 20, 0.0)  # (2)
+        ratio = float(np.linalg.norm(rec - volume) / np.linalg.norm(x0 - volume))
+        assert ratio < 0.2, ratio
+    finally:
+        native.set_threads(1)
 
 
 def test_host_generators_match_reference_golden():
