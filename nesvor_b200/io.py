@@ -44,8 +44,27 @@ _pickle_module.Unpickler = _Unpickler
 _pickle_module.load = lambda f, **kw: _Unpickler(f, **kw).load()
 
 
+def _export_mlp(flat: torch.Tensor, net) -> torch.Tensor:
+    """Inverse of `_adapt_mlp`: the kernels keep the first layer with 32 | 64 input columns, tcnn with the
+    input width padded to a multiple of 16; the extra columns only ever multiply zeros and are dropped on export, so that
+    `density_net.params` has tcnn's element count and layout."""
+    if not hasattr(net, "layer_shapes"):
+        return flat
+    o0, k0 = net.layer_shapes[0]
+    k_ref = (net.n_input_dims + 15) // 16 * 16
+    if k_ref >= k0:
+        return flat
+    w0 = flat[: o0 * k0].view(o0, k0)[:, :k_ref]
+    return torch.cat([w0.reshape(-1), flat[o0 * k0 :]])
+
+
 def save_model(path: str, inr: INR, mask: Volume, args: Namespace) -> None:
-    torch.save({"model": inr.state_dict(), "mask": mask, "args": args}, path)
+    """cli/io.py:36-46: {"model": state_dict, "mask": Volume, "args": Namespace}; the MLP parameters are written in tcnn's
+    16-padded layout (`_export_mlp`), which `load_model` widens again."""
+    state = dict(inr.state_dict())
+    if "density_net.params" in state:
+        state["density_net.params"] = _export_mlp(state["density_net.params"], inr.density_net)
+    torch.save({"model": state, "mask": mask, "args": args}, path)
 
 
 def _adapt_mlp(flat: torch.Tensor, net) -> torch.Tensor:

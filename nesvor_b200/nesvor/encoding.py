@@ -183,6 +183,7 @@ class FusedMLP(nn.Module):
         for (o, k), kin in zip(self.layer_shapes, logical_in):
             bound = math.sqrt(6.0 / (o + kin))  # Xavier uniform on the (16-padded) logical shape
             w = (torch.rand(o, k, generator=g, dtype=torch.float32) * 2 - 1) * bound
+            w[:, kin:] = 0  # columns beyond tcnn's 16-padded width only ever meet zero inputs: kept at zero (gradient 0, decay of 0)
             chunks.append(w.reshape(-1))
         self.params = nn.Parameter(torch.cat(chunks))
 

@@ -33,6 +33,28 @@ def test_save_load_round_trip(tmp_path):
     assert torch.equal(mask2.mask, mask.mask) and mask2.resolution_x == 0.8 and args2.width == 32
 
 
+def test_small_first_layer_is_written_in_the_16_padded_layout_and_round_trips(tmp_path):
+    """2 levels x 2 features = 4 inputs: the kernels keep 32 input columns, tcnn pads to 16: the file carries the
+    16-column first layer (64 x 16 + 64 x 16 = 2048 parameters here, not 64 x 32 + ...), and loading restores the module."""
+    from nesvor_b200.image import Volume
+    from nesvor_b200.io import load_model, save_model
+    from nesvor_b200.nesvor.models import INR
+    from nesvor_b200.transform import RigidTransform
+
+    args = _args(width=64)
+    inr = INR(torch.tensor([[-30.0, -30.0, -30.0], [30.0, 30.0, 30.0]]), args)
+    assert inr.encoding.n_levels * 2 <= 16 and inr.density_net.layer_shapes[0] == (64, 32)
+    with torch.no_grad():  # the padding columns multiply zeros: whatever they hold is immaterial and not stored
+        inr.density_net.weight_views()[0][:, 16:] = 0
+    mask = Volume(torch.ones(2, 2, 2), torch.ones(2, 2, 2, dtype=torch.bool), RigidTransform(torch.zeros(1, 6)), 1.0, 1.0, 1.0)
+    path = str(tmp_path / "m.pt")
+    save_model(path, inr, mask, args)
+    raw = torch.load(path, weights_only=False)["model"]["density_net.params"]
+    assert raw.numel() == 64 * 16 + 16 * 64
+    inr2, _, _ = load_model(path, torch.device("cpu"))
+    assert torch.equal(inr2.density_net.params, inr.density_net.params)
+
+
 def test_load_builds_the_network_from_the_checkpoints_own_args(tmp_path):
     """cli/io.py:24-29: INR(cp["model"]["bounding_box"], cp["args"]) -- the caller's namespace, which `inputs()` passes in
     full, must not change the architecture the stored parameters are decoded with (a different coarsest_resolution with
