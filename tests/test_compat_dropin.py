@@ -57,6 +57,12 @@ for name, call in (("axisangle2mat", lambda: rtc.axisangle2mat(ax)),
         errs[name] = str(e)[:60]
 out["errors"] = errs
 out["train_uses_ref_models"] = rtrain.NeSVoR is rm.NeSVoR
+# the hot loop: `train` is rebound to the fused adapter where the reference looks it up, the original is kept for the fallback
+import nesvor.cli.commands as cmds
+out["train_rebound"] = bool(getattr(rtrain.train, "__nesvor_b200_fused__", False)) and cmds.train is rtrain.train
+out["ref_train_kept"] = compat._REF_TRAIN is not None and compat._REF_TRAIN.__module__ == "nesvor.nesvor.train" and compat._REF_TRAIN is not rtrain.train
+compat.install()  # idempotent: a second call must not wrap the adapter around itself
+out["train_rebound_once"] = compat._REF_TRAIN.__module__ == "nesvor.nesvor.train" and cmds.train is rtrain.train
 # ---- the reference's own image module on the nibabel stand-in: write with the reference, read with both
 import os, tempfile
 import numpy as np
@@ -96,6 +102,7 @@ def test_unmodified_reference_runs_on_the_standin_modules(native_lib):
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert set(out["installed"]) >= {"nesvor.slice_acq_cuda", "nesvor.transform_convert_cuda", "tinycudann"}
     assert out["sa_is_ours"] and out["tc_is_ours"] and out["ref_file"].startswith(REF) and out["train_uses_ref_models"]
+    assert "nesvor.nesvor.train.train" in out["installed"] and out["train_rebound"] and out["ref_train_kept"] and out["train_rebound_once"]
     assert out["encoding_class"] == "HashGridEncoding" and out["network_class"] == "FusedMLP"
     assert out["state_keys"] == ["bounding_box", "density_net.params", "encoding.params"] and all(out["same_shapes"].values())
     assert out["n_levels"] == 12  # 110 mm box, reference defaults (SURVEY s.8: base 7, L 12)
