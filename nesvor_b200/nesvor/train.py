@@ -4,8 +4,9 @@ Host-side mirror of nesvor/nesvor/train.py: `Dataset` (:14-120: pixel table, `bo
 `get_batch` with full-table reshuffle at epoch end, `mask`) and `train(slices, args)` (:123-232:
 AdamW with two groups, MultiStepLR on milestones, GradScaler(init_scale=1), loss weights, logging
 of moving averages, outputs).  The per-iteration compute is delegated to `NeSVoR.forward`
-(autograd-composed native ops) or, when `args.fused` is set and the configuration is supported,
-to the fused kernel + fused AdamW (`fused.FusedTrainer`).
+(autograd-composed native ops under fp16 autocast, like the reference's loop) or, when `args.fused` is set, to the fused
+kernel + fused AdamW (`fused.FusedTrainer`); a configuration the fused kernels are not instantiated for falls back to the
+per-op path with a warning (single process; under data parallelism it raises).
 
 Data parallelism (the reference is single-GPU): when `torch.distributed` is initialised with more than
 one rank, `train` keeps the pixel table replicated, makes every rank draw the SAME global batch of `args.batch_size`
@@ -150,11 +151,20 @@ def train(slices: List[Slice], args: Namespace) -> Tuple[INR, List[Slice], Volum
         with torch.no_grad():  # replicas start from rank 0's initialisation (nn.Embedding draws from the global RNG)
             for p in model.parameters():
                 dist.broadcast(p.data, src=0)
+    first_losses = None
     if use_fused:
-        from .fused import FusedTrainer
+        from .fused import FusedTrainer, FusedUnsupported
 
-        trainer = FusedTrainer(model, args, batch_size=args.batch_size // world)
-    else:
+        try:  # the constructor checks the configuration, the first launch checks the kernel instantiations
+            trainer = FusedTrainer(model, args, batch_size=args.batch_size // world)
+            batch = dataset.get_batch(args.batch_size, args.device)
+            first_losses = (trainer.step_distributed(dist, world, **shard_batch(batch, rank, world)) if world > 1 else trainer.step(**batch))
+        except FusedUnsupported as e:
+            if world > 1:
+                raise
+            logging.warning("nesvor_b200: %s -- training on the per-op native path", e)
+            use_fused = False
+    if not use_fused:
         optimizer = build_optimizer(model, args)
         scheduler = optim.lr_scheduler.MultiStepLR(optimizer=optimizer, milestones=list(range(1, len(args.milestones) + 1)), gamma=args.gamma)
         fp16 = not args.single_precision
@@ -168,17 +178,20 @@ def train(slices: List[Slice], args: Namespace) -> Tuple[INR, List[Slice], Volum
     pending = None
     for i in range(1, args.n_iter + 1):
         t0 = time.time()
-        batch = dataset.get_batch(args.batch_size, args.device)
-        if world > 1:
-            losses = trainer.step_distributed(dist, world, **shard_batch(batch, rank, world))
+        if first_losses is not None:  # iteration 1 ran above (it doubles as the probe of the fused instantiations)
+            losses, first_losses = first_losses, None
+        elif world > 1:
+            losses = trainer.step_distributed(dist, world, **shard_batch(dataset.get_batch(args.batch_size, args.device), rank, world))
         elif use_fused:
-            losses = trainer.step(**batch)
+            losses = trainer.step(**dataset.get_batch(args.batch_size, args.device))
         else:
-            losses = model(**batch)
-            loss = 0
-            for k in losses:
-                if k in weights and weights[k]:
-                    loss = loss + weights[k] * losses[k]
+            batch = dataset.get_batch(args.batch_size, args.device)
+            with torch.autocast("cuda", dtype=torch.float16, enabled=fp16):  # train.py:183: forward and loss sum under autocast
+                losses = model(**batch)
+                loss = 0
+                for k in losses:
+                    if k in weights and weights[k]:
+                        loss = loss + weights[k] * losses[k]
             scaler.scale(loss).backward()
             if getattr(args, "debug", False):
                 for _name, _p in model.named_parameters():

@@ -144,3 +144,25 @@ def test_train_with_fused_bias_field_head(native_lib):
     assert not torch.equal(before, model.b_net.params.detach())
     ref = model(**dataset.get_batch(512, dev))
     assert torch.isfinite(ref["biasReg"]) and float(ref["biasReg"]) < 5e-2
+
+
+def test_train_falls_back_to_the_per_op_path_when_the_fused_kernels_do_not_cover_the_configuration(native_lib, caplog):
+    """`--depth 2` with the variance heads on has no fused instantiation (sigma_net with two hidden layers): `train()` with
+    args.fused must warn and run the reference's loop structure (fp16 autocast forward, GradScaler, torch AdamW, train.py:179-198)
+    on the per-op native kernels instead of raising; the model must still learn."""
+    import logging
+
+    import nesvor_b200 as nb
+    import psnr_phantom as pp
+    from nesvor_b200.data.phantom import simulate_slices
+
+    dev = torch.device("cuda", 0)
+    args = pp.make_args(dev, n_iter=60, batch_size=512, n_samples=32, depth=2, mask_threshold=0.1)
+    torch.manual_seed(0)
+    slices, _, _ = simulate_slices(device=dev, n=32, n_stacks=3, res_r=1.0, res_s=1.0, gap=2.0)
+    with caplog.at_level(logging.WARNING):
+        inr, out_slices, mask = nb.train(slices, args)
+    assert any("per-op native path" in r.getMessage() for r in caplog.records)
+    assert len(out_slices) == len(slices) and all(torch.isfinite(p).all() for p in inr.parameters())
+    x = torch.rand(256, 3, device=dev) * 10 - 5
+    assert torch.isfinite(inr(x[:, None], False)).all()
