@@ -129,15 +129,19 @@ def fused_impl(request):
     _lib.check(_lib.lib().nsv_set_fused_tc_groups(-1))
 
 
-@pytest.mark.parametrize("fused_impl", ["mma", "tcgen05", "tcgen05x3", "ws"], indirect=True)
-@pytest.mark.parametrize("name", list(CONFIGS))
+def _instantiated(name, impl):
+    """Which (configuration, implementation) pairs exist: the tcgen05 paths are instantiated for width 64 (UMMA M = 64 wgrad),
+    the bias-field head in the tcgen05 all-phases kernel only."""
+    if impl in ("tcgen05", "tcgen05x3", "ws") and CONFIGS[name].get("width", 64) != 64:
+        return False
+    return not (impl in ("mma", "ws") and CONFIGS[name].get("n_levels_bias", 0))
+
+
+@pytest.mark.parametrize("name,fused_impl", [(n, i) for n in CONFIGS for i in ("mma", "tcgen05", "tcgen05x3", "ws") if _instantiated(n, i)],
+                         indirect=["fused_impl"])
 def test_fused_train_step_parity(native_lib, name, fused_impl):
     from nesvor_b200.nesvor.fused import FusedState
 
-    if fused_impl in ("tcgen05", "tcgen05x3", "ws") and CONFIGS[name].get("width", 64) != 64:
-        pytest.skip("tcgen05 paths are instantiated for width 64 (UMMA M = 64 wgrad)")
-    if fused_impl in ("mma", "ws") and CONFIGS[name].get("n_levels_bias", 0):
-        pytest.skip("the bias-field head is instantiated in the tcgen05 all-phases kernel only")
     args = make_args(**CONFIGS[name])
     n_slices = 9
     model, om = build_pair(args, n_slices)
