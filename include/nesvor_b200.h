@@ -206,7 +206,9 @@ typedef struct nsv_inr_grads {    /* device pointers, all fp32, caller zero-fill
   float* slice_scale_c;           /* [n_slices]: receives dL/dlogit_coef (softmax chain rule applied by the finalize kernel) */
   float* log_var_slice;
   float* losses;                  /* [8]: [0] MSE, [1] logVar, [2] biasReg, [3] imageReg (final values);
-                                   * [4] INPUT when n_levels_bias > 0: mean(log_bias) over the whole batch, see nsv_inr_bias_mean */
+                                   * [4] INPUT when n_levels_bias > 0: mean(log_bias) over the whole batch, see nsv_inr_bias_mean;
+                                   * [5] transReg (written by nsv_trans_reg_f32 when the caller points it there); [6] = [0] + [1],
+                                   * the sum the reference logs as "MSE+logVar" (models.py:317-319); [7] unused */
 } nsv_inr_grads;
 
 /* number of fp16 elements of the packed MLP buffer and per-net offsets (host helper) */

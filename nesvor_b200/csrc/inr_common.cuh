@@ -613,6 +613,7 @@ static __global__ void __launch_bounds__(256) inr_finalize_kernel(const float* _
   }
   if (tid == 0 && image_reg == 2) losses[3] = delta * (losses[3] - 1.f);
   if (tid == 0 && n_levels_bias) losses[2] = losses[4] * losses[4];  // biasReg = mean(log_bias)^2 (models.py:323); [4] = the batch mean
+  if (tid == 0) losses[6] = losses[0] + losses[1];  // "MSE+logVar" as the reference logs it (models.py:317-319)
 }
 
 

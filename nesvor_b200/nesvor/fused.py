@@ -28,6 +28,9 @@ _IMAGE_REG = {"TV": 1, "edge": 2, "L2": 3}
 _SIGMA_Z_SLOT = 16  # packed sigma_net input = [slice embedding (16) | z0..z15]; z0's column is dead
 
 
+LOSS_RING = 4096  # iterations before a loss slot is reused (FusedState.next_losses)
+
+
 class FusedUnsupported(RuntimeError):
     """The configuration is outside what kernel A is instantiated for (use the unfused native path)."""
 
@@ -139,8 +142,12 @@ class FusedState:
         self.tail32: Optional[torch.Tensor] = None
         self.flat = torch.zeros(self.n_total, dtype=torch.float32, device=dev)
         self.flat16 = torch.zeros(self.n_total, dtype=torch.float16, device=dev)
-        self.grad = torch.zeros(self.n_total + 8, dtype=torch.float32, device=dev)  # + losses[8]
-        self.losses = self.grad[self.n_total : self.n_total + 8]
+        self.grad = torch.zeros(self.n_total + 8, dtype=torch.float32, device=dev)
+        # loss values: a ring of 8-float slots, one per iteration (`next_losses`), so that an iteration needs neither a memset of
+        # its slot nor a snapshot copy of it -- the whole ring is cleared once per LOSS_RING iterations
+        self.loss_ring = torch.zeros(LOSS_RING, 8, dtype=torch.float32, device=dev)
+        self.loss_slot = 0
+        self.losses = self.loss_ring[0]
         self.psf_sigma = model.psf_sigma.contiguous().float() if model is not None else None
         self.pull_from_model()
 
@@ -168,7 +175,6 @@ class FusedState:
             tail32 = buf[n_grad_pad + n_f16_pad : n_grad_pad + n_f16_pad + n_tail * 4].view(torch.float32)
             tail32.copy_(self.flat[self.tail_lo :])
             self.tail32 = tail32
-        self.losses = self.grad[self.n_total : self.n_total + 8]
         self._symm_buf, self.peer_handle = buf, handle
         world = handle.world_size
         ptrs = [int(p) for p in handle.buffer_ptrs]
@@ -184,7 +190,6 @@ class FusedState:
     def disable_peer_memory(self) -> None:
         """Back to private buffers (another rank could not set peer memory up: the ranks fall back together)."""
         self.grad, self.flat16 = self.grad.clone(), self.flat16.clone()
-        self.losses = self.grad[self.n_total : self.n_total + 8]
         self.tail32 = None
         self._symm_buf = self.peer_handle = self.peer_grads = self.peer_flat16 = self.peer_tail32 = self.peer_flags = self.dp_flags = None
 
@@ -304,12 +309,24 @@ class FusedState:
             g0[:, _SIGMA_Z_SLOT] = 0
         return self.losses, v_out
 
+    def next_losses(self) -> torch.Tensor:
+        """Binds `self.losses` to the next (zeroed) slot of the ring and returns it.  Slots handed out earlier keep their values
+        until the ring wraps, LOSS_RING - 1 iterations later -- long enough for every consumer here (train(), compat.fused_train
+        and the benchmark read an iteration's values one iteration later)."""
+        self.loss_slot += 1
+        if self.loss_slot == self.loss_ring.shape[0]:
+            self.loss_ring.zero_()
+            self.loss_slot = 0
+        self.losses = self.loss_ring[self.loss_slot]
+        return self.losses
+
     def loss_dict(self, losses: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Views into `losses` (no device work) under the reference's names; [6] = MSE + logVar is written by the finalize kernel."""
         a = self.args
         out = {D_LOSS: losses[0]}
         if not (a.no_pixel_variance and a.no_slice_variance):
             out[S_LOSS] = losses[1]
-            out[DS_LOSS] = losses[0] + losses[1]
+            out[DS_LOSS] = losses[6]
         if a.n_levels_bias:
             out[B_REG] = losses[2]
         out[I_REG] = losses[3]
@@ -322,12 +339,87 @@ class LossHandle:
     THAT copy has landed, so a loop that reads iteration i's losses after enqueueing iteration i + 1 (train() below does)
     keeps one iteration of work queued on the GPU instead of draining it at every `.item()` (train.py:199-200)."""
 
-    def __init__(self, keys, host: torch.Tensor, event: torch.cuda.Event):
+    def __init__(self, keys, host: torch.Tensor, event: torch.cuda.Event, pos=None):
         self.keys, self.host, self.event = keys, host, event
+        self.pos = list(range(len(keys))) if pos is None else pos
 
     def get(self) -> Dict[str, float]:
         self.event.synchronize()
-        return dict(zip(self.keys, self.host.tolist()))
+        vals = self.host.tolist()
+        return {k: vals[i] for k, i in zip(self.keys, self.pos)}
+
+
+class HostBatchFeeder:
+    """Batches that live in (pinned) HOST memory, delivered to the device one iteration ahead of the compute stream.
+
+    The reference keeps its whole pixel table on the GPU (train.py:14-75), so its loop never copies a batch; a caller whose table
+    does not fit, or who produces batches on the host, would pay three small in-stream copies in front of every iteration
+    (~0.03 ms of a 0.8 ms iteration, bench.py's `e2e` leg in round 1).  Here the copies of batch i + 1 run on a side stream
+    while the kernels of batch i execute: `depth` device slots, a `ready` event per slot that the compute stream waits on, a `free`
+    event per slot that the copy stream waits on before overwriting it.
+
+        for batch in feeder.feed(host_batches):      # dicts of CPU tensors, same keys / shapes from batch to batch
+            losses = trainer.step(**batch)            # device tensors, valid until the loop asks for the next batch
+    """
+
+    def __init__(self, device, depth: int = 2):
+        self.device = torch.device(device)
+        self.depth = max(2, int(depth))
+        self.stream = torch.cuda.Stream(self.device)
+        self._slots = [None] * self.depth
+        self._ready = [torch.cuda.Event() for _ in range(self.depth)]
+        self._free = [None] * self.depth
+        self._head = self._tail = 0
+        self.bytes_copied = 0
+
+    def push(self, host_batch: Dict[str, torch.Tensor]) -> None:
+        """Enqueues the copy of one host batch into the next free slot (side stream)."""
+        if self._head - self._tail >= self.depth:
+            raise RuntimeError("HostBatchFeeder: every slot holds a batch that has not been released")
+        k = self._head % self.depth
+        self._head += 1
+        with torch.cuda.stream(self.stream):
+            if self._free[k] is not None:
+                self.stream.wait_event(self._free[k])  # the iteration that read this slot last has finished
+            slot = self._slots[k]
+            if slot is None or slot.keys() != host_batch.keys() or any(slot[n].shape != t.shape or slot[n].dtype != t.dtype for n, t in host_batch.items()):
+                slot = self._slots[k] = {n: torch.empty(t.shape, dtype=t.dtype, device=self.device) for n, t in host_batch.items()}
+            for n, t in host_batch.items():
+                slot[n].copy_(t, non_blocking=True)
+                self.bytes_copied += t.numel() * t.element_size()
+            self._ready[k].record(self.stream)
+
+    def pop(self):
+        """(slot id, device batch) of the oldest pushed batch; the CURRENT stream waits for its copy, the host does not."""
+        if self._tail >= self._head:
+            raise RuntimeError("HostBatchFeeder: nothing pushed")
+        k = self._tail % self.depth
+        torch.cuda.current_stream(self.device).wait_event(self._ready[k])
+        return k, self._slots[k]
+
+    def release(self, k: int) -> None:
+        """To be called once every kernel that reads slot `k` has been enqueued on the current stream."""
+        ev = self._free[k] if self._free[k] is not None else torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._free[k] = ev
+        self._tail += 1
+
+    def feed(self, host_batches):
+        """Generator over device batches; the copy of the next batch is enqueued before the current one is handed out."""
+        it = iter(host_batches)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        self.push(nxt)
+        while True:
+            k, batch = self.pop()
+            nxt = next(it, None)
+            if nxt is not None:
+                self.push(nxt)
+            yield batch
+            self.release(k)
+            if nxt is None:
+                return
 
 
 class FusedTrainer:
@@ -380,17 +472,27 @@ class FusedTrainer:
         self.lr *= gamma
 
     def losses_to_host(self, losses: Dict[str, torch.Tensor]) -> LossHandle:
-        """Enqueues ONE device-to-host copy of a step's loss values (pinned ring buffer) and returns its handle."""
+        """Enqueues ONE device-to-host copy of a step's loss values (pinned ring buffer) and returns its handle.  For the dict
+        `step` returned (views into one slot of the loss ring) that is the copy engine alone: no gather kernel."""
         if not hasattr(self, "_host_ring"):
             self._host_ring = [torch.empty(8, dtype=torch.float32).pin_memory() for _ in range(4)]
             self._host_i = 0
         keys = list(losses.keys())
-        host = self._host_ring[self._host_i % len(self._host_ring)][: len(keys)]
+        host = self._host_ring[self._host_i % len(self._host_ring)]
         self._host_i += 1
-        host.copy_(torch.stack([losses[k].reshape(()) for k in keys]), non_blocking=True)
+        slot = self.state.losses
+        pos = [losses[k].storage_offset() - slot.storage_offset() for k in keys]
+        same = all(losses[k].untyped_storage().data_ptr() == slot.untyped_storage().data_ptr() and 0 <= i < 8 for k, i in zip(keys, pos))
+        if same:
+            host.copy_(slot, non_blocking=True)
+        else:  # values computed elsewhere (e.g. the per-op path): gather them first
+            pos = list(range(len(keys)))
+            host[: len(keys)].copy_(torch.stack([losses[k].reshape(()).float() for k in keys]), non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.state.device))
-        return LossHandle(keys, host, ev)
+        h = LossHandle(keys, host, ev, pos)
+        h.nbytes = 4 * (host.numel() if same else len(keys))  # what the copy moved
+        return h
 
     def _trans_reg(self) -> None:
         """transReg (models.py:357-363) and its gradient in one native launch (`nsv_trans_reg_f32`): the weighted gradient is
@@ -408,15 +510,14 @@ class FusedTrainer:
     def step(self, xyz, v, slice_idx, noise=None) -> Dict[str, torch.Tensor]:
         st, a = self.state, self.args
         self.iteration += 1
-        st.losses.zero_()  # parameter gradients were cleared by the previous AdamW pass
+        st.next_losses()  # a zeroed slot of the loss ring; the parameter gradients were cleared by the previous AdamW pass
         n_q = xyz.shape[0] * a.n_samples
         losses, _ = st.forward_backward(xyz, v, slice_idx, noise, seed=self.seed, offset=(self.iteration - 1) * n_q)
         if self.pose and a.weight_transformation:
             self._trans_reg()
-        snap = losses.clone()  # one copy of the step's loss values (the buffer is cleared by the next step)
-        out = st.loss_dict(snap)
+        out = st.loss_dict(losses)
         if self.pose and a.weight_transformation:
-            out[T_REG] = snap[5]
+            out[T_REG] = losses[5]
         with torch.cuda.device(st.device):
             rc = _lib.lib().nsv_adamw_step(
                 _lib.ptr(st.flat), _lib.ptr(st.grad), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), _lib.ptr(st.flat16),
@@ -433,17 +534,16 @@ class FusedTrainer:
         if self.dp_mode is None:
             self._setup_dp(dist, world)
         self.iteration += 1
-        st.losses.zero_()
+        st.next_losses()
         n_q = xyz.shape[0] * a.n_samples
         rank = dist.get_rank()
         losses, _ = st.forward_backward(xyz, v, slice_idx, noise, seed=self.seed + 7919 * rank,
                                         offset=(self.iteration - 1) * n_q, dist=dist, world=world)
         if self.pose and a.weight_transformation:
             self._trans_reg()  # identical on every rank: the all-reduce mean leaves it unchanged
-        snap = losses.clone()
-        out = st.loss_dict(snap)
+        out = st.loss_dict(losses)
         if self.pose and a.weight_transformation:
-            out[T_REG] = snap[5]
+            out[T_REG] = losses[5]
         self._dp_update(dist, world)
         return out
 

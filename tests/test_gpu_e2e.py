@@ -166,3 +166,69 @@ def test_train_falls_back_to_the_per_op_path_when_the_fused_kernels_do_not_cover
     assert len(out_slices) == len(slices) and all(torch.isfinite(p).all() for p in inr.parameters())
     x = torch.rand(256, 3, device=dev) * 10 - 5
     assert torch.isfinite(inr(x[:, None], False)).all()
+
+
+def test_host_batch_feeder_and_loss_ring(native_lib):
+    """Host-resident batches through HostBatchFeeder (copies one iteration ahead on a side stream) give the same iterations as
+    device-resident batches, bit for bit on the first step and within atomics noise later; the loss values come back through ONE
+    32-byte copy per step (LossHandle) and equal the device values; "MSE+logVar" is the sum the finalize kernel wrote; the loss
+    ring survives a wrap-around."""
+    import nesvor_b200 as nb
+    import psnr_phantom as pp
+    from nesvor_b200.data.phantom import simulate_slices
+    from nesvor_b200.nesvor import fused as F
+    from nesvor_b200.nesvor.train import Dataset
+
+    dev = torch.device("cuda", 0)
+    args = pp.make_args(dev, n_iter=10, batch_size=1024, n_samples=64)
+    args.no_slice_variance = False  # MSE, logVar and their sum
+    torch.manual_seed(0)
+    slices, _, _ = simulate_slices(device=dev, n=32, n_stacks=3, res_r=1.0, res_s=1.0, gap=2.0)
+    dataset = Dataset(slices, args)
+    batches = [dataset.get_batch(args.batch_size, dev) for _ in range(12)]
+    batches = [{k: v.clone() for k, v in b.items()} for b in batches]
+    host = [{k: v.cpu().pin_memory() for k, v in b.items()} for b in batches]
+
+    def run(feed):
+        torch.manual_seed(1)
+        model = nb.NeSVoR(dataset.transformation, dataset.resolution, dataset.mean, dataset.bounding_box, args)
+        tr = F.FusedTrainer(model, args)
+        got, handles = [], []
+        for batch in feed:
+            out = tr.step(**batch)
+            handles.append((tr.losses_to_host(out), {k: v for k, v in out.items()}))
+        torch.cuda.synchronize()
+        for h, out in handles:
+            vals = h.get()
+            assert h.nbytes == 32 and set(vals) == set(out)
+            for k in out:
+                assert vals[k] == float(out[k]), k  # the host copy IS the device value (slots are not reused within the ring)
+            assert abs(vals["MSE+logVar"] - (vals["MSE"] + vals["logVar"])) <= 1e-6 * max(1.0, abs(vals["MSE"]))
+            got.append(vals)
+        return got, tr
+
+    a, _ = run(batches)
+    feeder = F.HostBatchFeeder(dev)
+    b, tr = run(feeder.feed(host))
+    assert feeder.bytes_copied == 12 * args.batch_size * (12 + 4 + 8)
+    assert a[0]["MSE"] == pytest.approx(b[0]["MSE"], rel=1e-6)
+    for x, y in zip(a, b):
+        for k in x:
+            assert y[k] == pytest.approx(x[k], rel=2e-3, abs=1e-6), k  # same batches, same seeds: atomics-order noise only
+    # delivery order under overlap: every slot is overwritten only after the step that read it; tag batches by their first value
+    tags = []
+    slow = torch.randn(2048, 2048, device=dev)
+    for batch in F.HostBatchFeeder(dev, depth=2).feed(host):
+        (slow @ slow).sum()  # keeps the compute stream busy while the next copy is in flight
+        tags.append(batch["v"][:4].clone())
+    torch.cuda.synchronize()
+    for t, hb in zip(tags, host):
+        assert torch.equal(t.cpu(), hb["v"][:4])
+    # wrap-around of the loss ring: values of the step after the wrap are right, the ring was cleared once
+    st = tr.state
+    st.loss_slot = F.LOSS_RING - 2
+    o1 = tr.step(**batches[0])
+    v1 = float(o1["MSE"])
+    o2 = tr.step(**batches[1])  # wraps: ring cleared, slot 0
+    assert st.loss_slot == 0 and float(o2["MSE"]) > 0 and float(o1["MSE"]) == 0.0 and v1 > 0
+    assert float(st.loss_ring[1:].abs().sum()) == 0.0
