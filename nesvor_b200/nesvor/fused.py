@@ -148,6 +148,7 @@ class FusedState:
         self.loss_ring = torch.zeros(LOSS_RING, 8, dtype=torch.float32, device=dev)
         self.loss_slot = 0
         self.losses = self.loss_ring[0]
+        self.last_readback: Optional[torch.cuda.Event] = None
         self.psf_sigma = model.psf_sigma.contiguous().float() if model is not None else None
         self.pull_from_model()
 
@@ -315,6 +316,8 @@ class FusedState:
         and the benchmark read an iteration's values one iteration later)."""
         self.loss_slot += 1
         if self.loss_slot == self.loss_ring.shape[0]:
+            if self.last_readback is not None:  # a read-back stream may still be copying the newest slot (losses_to_host)
+                torch.cuda.current_stream(self.device).wait_event(self.last_readback)
             self.loss_ring.zero_()
             self.loss_slot = 0
         self.losses = self.loss_ring[self.loss_slot]
@@ -483,13 +486,25 @@ class FusedTrainer:
         slot = self.state.losses
         pos = [losses[k].storage_offset() - slot.storage_offset() for k in keys]
         same = all(losses[k].untyped_storage().data_ptr() == slot.untyped_storage().data_ptr() and 0 <= i < 8 for k, i in zip(keys, pos))
+        ev = torch.cuda.Event()
+        cur = torch.cuda.current_stream(self.state.device)
         if same:
-            host.copy_(slot, non_blocking=True)
+            # the slot stays untouched for LOSS_RING iterations, so its copy need not sit in the compute stream: a read-back
+            # stream waits for the iteration's last kernel and copies while the next iteration's kernels already run
+            if not hasattr(self, "_rb_stream"):
+                self._rb_stream = torch.cuda.Stream(self.state.device)
+                self._rb_done = [torch.cuda.Event() for _ in self._host_ring]
+            done = self._rb_done[self._host_i % len(self._rb_done)]
+            done.record(cur)
+            with torch.cuda.stream(self._rb_stream):
+                self._rb_stream.wait_event(done)
+                host.copy_(slot, non_blocking=True)
+                ev.record(self._rb_stream)
+            self.state.last_readback = ev
         else:  # values computed elsewhere (e.g. the per-op path): gather them first
             pos = list(range(len(keys)))
             host[: len(keys)].copy_(torch.stack([losses[k].reshape(()).float() for k in keys]), non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.state.device))
+            ev.record(cur)
         h = LossHandle(keys, host, ev, pos)
         h.nbytes = 4 * (host.numel() if same else len(keys))  # what the copy moved
         return h
