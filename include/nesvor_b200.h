@@ -291,6 +291,18 @@ int nsv_adamw_step_dp(float* param, const void* const* peer_grads, float* exp_av
                       void* const* peer_param_f16, int world, int rank, int64_t n, float lr, float beta1, float beta2,
                       float eps, float weight_decay, int step, float grad_unscale,
                       int64_t f32_lo /* multiple of 4 */, void* const* peer_param_f32 /* or NULL */, void* stream);
+/* The same step with the NVSwitch doing the sum and the replication (NVLS): `mc_grad`, `mc_param_f16`, `mc_param_f32` are the
+ * MULTICAST addresses of the three peer buffers (one address bound to the copy on every rank, e.g. the `multicast_ptr` of a
+ * torch symmetric-memory allocation plus the buffer's offset).  Each owner reads its shard's gradient sum with
+ * multimem.ld_reduce (one shard of inbound link traffic per rank and step instead of world - 1) and writes the refreshed
+ * parameters with multimem.st (one shard outbound instead of world - 1).  The switch's summation order is not the rank order of
+ * nsv_adamw_step_dp, so the two differ by fp32 round-off; replicas still agree bit for bit with each other (one owner per
+ * element).  The unicast peer pointers are still needed (ragged tail of the last shard).  Same barriers around it. */
+int nsv_adamw_step_dp_mc(float* param, const void* const* peer_grads, float* exp_avg, float* exp_avg_sq,
+                         void* const* peer_param_f16, int world, int rank, int64_t n, float lr, float beta1, float beta2,
+                         float eps, float weight_decay, int step, float grad_unscale, int64_t f32_lo,
+                         void* const* peer_param_f32, const void* mc_grad, void* mc_param_f16, void* mc_param_f32 /* or NULL */,
+                         void* stream);
 /* The same kernel with the rendezvous of the ranks INSIDE it (no host-launched barrier around it): `peer_flags[r]` = rank r's
  * flag block (64 x uint64 in peer-accessible memory, zero-initialised once and made visible to all ranks before the first
  * call), `epoch` = a positive number that is the same on every rank for a given step and strictly increases from step to

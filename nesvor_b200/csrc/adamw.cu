@@ -78,7 +78,26 @@ struct PeerPtrs {
   // [16,32) "rank i has read every gradient and written every fp16 / fp32 copy", [32] block ticket counter, [33] time-out marker,
   // [34] device-scope "every rank's gradient is complete" (written by block 0 of this rank)
   unsigned long long* flags[kMaxPeers];
+  // optional NVSwitch multicast addresses of the same three buffers (one address = the copy on every rank): with them the gradient
+  // sum is ONE multimem.ld_reduce per vector (the switch adds the ranks' values: a shard's worth of inbound traffic instead of
+  // world - 1 shards) and the refreshed parameters are ONE multimem.st (the switch replicates it)
+  const float* mc_grad;
+  __half* mc_p16;
+  float* mc_p32;
 };
+
+__device__ __forceinline__ float4 multimem_sum_f32x4(const float* mc) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc) : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_store_f32x4(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void multimem_store_f16x4(__half* mc, uint2 packed) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f16x2 [%0], {%1, %2};" ::"l"(mc), "r"(packed.x), "r"(packed.y) : "memory");
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -148,7 +167,9 @@ __global__ void __launch_bounds__(256) adamw_dp_kernel(float* __restrict__ p, co
   for (int64_t i = tid; i < n4; i += nth) {
     const int64_t e = lo + 4 * i;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (WORLD > 0) {
+    if (peers.mc_grad) {
+      g = multimem_sum_f32x4(peers.mc_grad + e);
+    } else if (WORLD > 0) {
       float4 gr[WORLD > 0 ? WORLD : 1];
 #pragma unroll
       for (int r = 0; r < WORLD; ++r) gr[r] = *reinterpret_cast<const float4*>(peers.grad[r] + e);
@@ -178,6 +199,11 @@ __global__ void __launch_bounds__(256) adamw_dp_kernel(float* __restrict__ p, co
     *reinterpret_cast<float4*>(v + e) = vv;
     const __half2 h0 = __floats2half2_rn(pv.x, pv.y), h1 = __floats2half2_rn(pv.z, pv.w);
     const uint2 packed = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    if (peers.mc_grad) {
+      multimem_store_f16x4(peers.mc_p16 + e, packed);
+      if (e >= f32_lo) multimem_store_f32x4(peers.mc_p32 + (e - f32_lo), pv);
+      continue;
+    }
     for (int r = 0; r < world; ++r) *reinterpret_cast<uint2*>(peers.p16[r] + e) = packed;
     if (e >= f32_lo)  // f32_lo and lo are multiples of 4: a vector never straddles the boundary
       for (int r = 0; r < world; ++r) *reinterpret_cast<float4*>(peers.p32[r] + (e - f32_lo)) = pv;
@@ -228,7 +254,8 @@ extern "C" int nsv_adamw_shard_bounds(int64_t n, int world, int rank, int64_t* l
 static int adamw_step_dp_impl(float* param, const void* const* peer_grads, float* exp_avg, float* exp_avg_sq,
                              void* const* peer_param_f16, int world, int rank, int64_t n, float lr, float beta1, float beta2,
                              float eps, float weight_decay, int step, float grad_unscale, int64_t f32_lo,
-                             void* const* peer_param_f32, void* const* peer_flags, uint64_t epoch, int sync_mode, void* stream) {
+                             void* const* peer_param_f32, void* const* peer_flags, uint64_t epoch, int sync_mode, void* stream,
+                             const void* mc_grad = nullptr, void* mc_param_f16 = nullptr, void* mc_param_f32 = nullptr) {
   using namespace nsv;
   NSV_REQUIRE(n >= 0 && step >= 1, "nsv_adamw_step_dp: bad n / step");
   NSV_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "nsv_adamw_step_dp: world must be 1..16, rank in [0, world)");
@@ -236,6 +263,14 @@ static int adamw_step_dp_impl(float* param, const void* const* peer_grads, float
   if (!peer_param_f32) f32_lo = n;  // no fp32 mirror
   NSV_REQUIRE(f32_lo >= 0 && f32_lo % 4 == 0, "nsv_adamw_step_dp: f32_lo must be a non-negative multiple of 4");
   PeerPtrs pp;
+  pp.mc_grad = (const float*)mc_grad;
+  pp.mc_p16 = (__half*)mc_param_f16;
+  pp.mc_p32 = (float*)mc_param_f32;
+  if (mc_grad) {
+    NSV_REQUIRE(mc_param_f16 && (f32_lo >= n || mc_param_f32), "nsv_adamw_step_dp_mc: NULL multicast pointer");
+    NSV_REQUIRE(((uintptr_t)mc_grad | (uintptr_t)mc_param_f32) % 16 == 0 && (uintptr_t)mc_param_f16 % 8 == 0,
+                "nsv_adamw_step_dp_mc: multicast buffers must be 16-byte aligned (fp16 copy: 8-byte)");
+  }
   for (int r = 0; r < kMaxPeers; ++r) {
     pp.grad[r] = r < world ? (const float*)peer_grads[r] : nullptr;
     pp.p16[r] = r < world ? (__half*)peer_param_f16[r] : nullptr;
@@ -269,6 +304,17 @@ extern "C" int nsv_adamw_step_dp(float* param, const void* const* peer_grads, fl
                                  void* const* peer_param_f32, void* stream) {
   return adamw_step_dp_impl(param, peer_grads, exp_avg, exp_avg_sq, peer_param_f16, world, rank, n, lr, beta1, beta2, eps, weight_decay,
                             step, grad_unscale, f32_lo, peer_param_f32, nullptr, 0, 0, stream);
+}
+
+extern "C" int nsv_adamw_step_dp_mc(float* param, const void* const* peer_grads, float* exp_avg, float* exp_avg_sq,
+                                    void* const* peer_param_f16, int world, int rank, int64_t n, float lr, float beta1, float beta2,
+                                    float eps, float weight_decay, int step, float grad_unscale, int64_t f32_lo,
+                                    void* const* peer_param_f32, const void* mc_grad, void* mc_param_f16, void* mc_param_f32,
+                                    void* stream) {
+  using namespace nsv;
+  NSV_REQUIRE(mc_grad, "nsv_adamw_step_dp_mc: needs the multicast address of the gradient buffers");
+  return adamw_step_dp_impl(param, peer_grads, exp_avg, exp_avg_sq, peer_param_f16, world, rank, n, lr, beta1, beta2, eps, weight_decay,
+                            step, grad_unscale, f32_lo, peer_param_f32, nullptr, 0, 0, stream, mc_grad, mc_param_f16, mc_param_f32);
 }
 
 extern "C" int nsv_adamw_step_dp_sync(float* param, const void* const* peer_grads, float* exp_avg, float* exp_avg_sq,

@@ -140,6 +140,7 @@ class FusedState:
         # optimiser every rank keeps a current fp32 mirror of them (`tail32`, see enable_peer_memory / seg)
         self.tail_lo = (self.offsets["mlp"].stop + 3) // 4 * 4
         self.tail32: Optional[torch.Tensor] = None
+        self.mc_ptrs = None  # multicast addresses of (gradient, fp16 copy, fp32 tail mirror) once peer memory is on
         self.flat = torch.zeros(self.n_total, dtype=torch.float32, device=dev)
         self.flat16 = torch.zeros(self.n_total, dtype=torch.float16, device=dev)
         self.grad = torch.zeros(self.n_total + 8, dtype=torch.float32, device=dev)
@@ -185,6 +186,10 @@ class FusedState:
         self.dp_flags = buf[n_grad_pad + n_f16_pad + n_tail_pad :].view(torch.int64)
         self.dp_flags.zero_()
         self.peer_flags = (ctypes.c_void_p * world)(*[p + n_grad_pad + n_f16_pad + n_tail_pad for p in ptrs])
+        # NVSwitch multicast address of the same allocation (0 when the fabric / driver has no multicast support): lets the
+        # optimiser kernel sum the gradients and replicate the parameters inside the switch (nsv_adamw_step_dp_mc)
+        mc = int(getattr(handle, "multicast_ptr", 0) or 0)
+        self.mc_ptrs = (mc, mc + n_grad_pad, (mc + n_grad_pad + n_f16_pad) if n_tail > 0 else 0) if mc else None
         torch.cuda.synchronize(self.device)
         handle.barrier()  # every rank's copy is initialised before anyone's optimiser writes into it
 
@@ -193,6 +198,7 @@ class FusedState:
         self.grad, self.flat16 = self.grad.clone(), self.flat16.clone()
         self.tail32 = None
         self._symm_buf = self.peer_handle = self.peer_grads = self.peer_flat16 = self.peer_tail32 = self.peer_flags = self.dp_flags = None
+        self.mc_ptrs = None
 
     # ------------------------------------------------------------------ model <-> flat
     def seg(self, name: str, buf: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
@@ -594,14 +600,30 @@ class FusedTrainer:
             return
         if self.dp_mode == "peer":
             h = st.peer_handle
+            if getattr(self.args, "dp_multimem", None) is None:
+                import os
+
+                # in-switch reduction / replication (NVLS) whenever the symmetric allocation has a multicast address;
+                # NSV_DP_MULTIMEM=0 keeps the unicast peer loads / stores
+                self.args.dp_multimem = os.environ.get("NSV_DP_MULTIMEM", "1") != "0"
+            mc = st.mc_ptrs if self.args.dp_multimem else None
             h.barrier()  # every rank's kernel A has finished: all gradients are complete
             with torch.cuda.device(st.device):
-                rc = _lib.lib().nsv_adamw_step_dp(
-                    _lib.ptr(st.flat), st.peer_grads, _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), st.peer_flat16,
-                    ctypes.c_int(world), ctypes.c_int(rank), ctypes.c_int64(st.n_train), ctypes.c_float(self.lr), ctypes.c_float(0.9),
-                    ctypes.c_float(0.99), ctypes.c_float(1e-15), ctypes.c_float(1e-2), ctypes.c_int(self.iteration),
-                    ctypes.c_float(1.0 / world), ctypes.c_int64(st.tail_lo), st.peer_tail32, _lib.stream(st.device))
-            _lib.check(rc, "nsv_adamw_step_dp")
+                if mc is not None:
+                    rc = _lib.lib().nsv_adamw_step_dp_mc(
+                        _lib.ptr(st.flat), st.peer_grads, _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), st.peer_flat16,
+                        ctypes.c_int(world), ctypes.c_int(rank), ctypes.c_int64(st.n_train), ctypes.c_float(self.lr), ctypes.c_float(0.9),
+                        ctypes.c_float(0.99), ctypes.c_float(1e-15), ctypes.c_float(1e-2), ctypes.c_int(self.iteration),
+                        ctypes.c_float(1.0 / world), ctypes.c_int64(st.tail_lo), st.peer_tail32, ctypes.c_void_p(mc[0]),
+                        ctypes.c_void_p(mc[1]), ctypes.c_void_p(mc[2] or None), _lib.stream(st.device))
+                else:
+                    rc = _lib.lib().nsv_adamw_step_dp(
+                        _lib.ptr(st.flat), st.peer_grads, _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), st.peer_flat16,
+                        ctypes.c_int(world), ctypes.c_int(rank), ctypes.c_int64(st.n_train), ctypes.c_float(self.lr), ctypes.c_float(0.9),
+                        ctypes.c_float(0.99), ctypes.c_float(1e-15), ctypes.c_float(1e-2), ctypes.c_int(self.iteration),
+                        ctypes.c_float(1.0 / world), ctypes.c_int64(st.tail_lo), st.peer_tail32, _lib.stream(st.device))
+            _lib.check(rc, "nsv_adamw_step_dp_mc" if mc is not None else "nsv_adamw_step_dp")
+            self.dp_multimem_active = mc is not None
             h.barrier()  # every owner has read this rank's gradient and written this rank's fp16 parameters
             st.grad[: st.n_train].zero_()
             return
