@@ -603,9 +603,11 @@ class FusedTrainer:
             if getattr(self.args, "dp_multimem", None) is None:
                 import os
 
-                # in-switch reduction / replication (NVLS) whenever the symmetric allocation has a multicast address;
-                # NSV_DP_MULTIMEM=0 keeps the unicast peer loads / stores
-                self.args.dp_multimem = os.environ.get("NSV_DP_MULTIMEM", "1") != "0"
+                # in-switch reduction / replication (NVLS, nsv_adamw_step_dp_mc) is opt-in (NSV_DP_MULTIMEM=1): bit-identical to the
+                # unicast kernel at 2 ranks but slower there (exchange 0.122 vs 0.086 ms on config 2, profiles/r02_dp_multimem_2gpu.json)
+                # -- a reduce-scatter sends (world-1)/world of every rank's gradient whichever side does the adding, so the switch only
+                # relieves the receiving direction, and multimem.ld_reduce has the longer latency
+                self.args.dp_multimem = os.environ.get("NSV_DP_MULTIMEM", "0") == "1"
             mc = st.mc_ptrs if self.args.dp_multimem else None
             h.barrier()  # every rank's kernel A has finished: all gradients are complete
             with torch.cuda.device(st.device):
