@@ -209,7 +209,11 @@ def fused_train(slices, args):
     model.train()
     keys = list(first.keys())
     alpha = 1 - 0.001
-    ema = torch.zeros(len(keys), dtype=torch.float32, device=args.device)
+    # moving average (logger.py's) of the whole 8-float loss slot, one lerp kernel per iteration; the columns the log prints are
+    # picked when a line is due (`first`'s values are views into the slot: their storage offsets name the columns)
+    slot0 = trainer.state.losses
+    cols = [first[k].storage_offset() - slot0.storage_offset() for k in keys]
+    ema = torch.zeros(8, dtype=torch.float32, device=args.device)
     train_logger = None
     logging.info("NeSVoR training starts (nesvor_b200 fused iteration).")
     torch.cuda.synchronize(args.device)
@@ -219,11 +223,12 @@ def fused_train(slices, args):
         if i > 1:
             batch = dataset.get_batch(args.batch_size, args.device)
             losses = trainer.step(**batch)
-        ema.mul_(alpha).add_(torch.stack([losses[k] for k in keys]), alpha=1 - alpha)
+        ema.lerp_(trainer.state.losses, 1 - alpha)  # ema = alpha * ema + (1 - alpha) * losses
         if (decay_milestones and i >= decay_milestones[0]) or i == args.n_iter:
             if train_logger is None:
                 train_logger = rt.TrainLogger("time", "epoch", "iter", *keys, "lr")
-            avg = (ema / (1 - alpha**i)).tolist()  # the only device read-back of the loop
+            full = (ema / (1 - alpha**i)).tolist()  # the only device read-back of the loop
+            avg = [full[c] for c in cols]
             train_logger.log(datetime.timedelta(seconds=int(time.time() - t_start)), dataset.epoch, i, *avg, trainer.lr)
             if i < args.n_iter:
                 decay_milestones.pop(0)
