@@ -387,7 +387,8 @@ def run_ours(a):
         return trainer.step_distributed(dist, world, **batch)
 
     # ---------------- value: device-resident inputs, whole iteration (fwd + bwd + AdamW) ----------
-    for _ in range(max(a.warmup, 3)):
+    n_warm = max(a.warmup, 20)  # at least 20 untimed iterations (16 ms): clocks and the L2-resident table settle before the timed region
+    for _ in range(n_warm):
         one_step(dataset.get_batch(B, dev))
     sync_all()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -429,7 +430,7 @@ def run_ours(a):
             pending = handle
         return pending.get(), pending.nbytes
 
-    e2e_steps(max(a.warmup, 3))  # untimed warm-up of THIS path (side streams, pinned buffers and feeder slots are set up here)
+    e2e_steps(n_warm)  # untimed warm-up of THIS path (side streams, pinned buffers and feeder slots are set up here)
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     h2d0 = feeder.bytes_copied
@@ -517,7 +518,7 @@ def run_ours(a):
             pass
 
     cpu = cpu_oracle_throughput(steps=2, warmup=1) if world == 1 else None  # rank 0 at N = 1 only: two full config-2 iterations
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": n_warm,
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
             "data": "synthetic", "config": config_block(world, a.scaling, B if strong else None),
             "workload_detail": {"n_pixels_in_table": int(dataset.xyz.shape[0]), "n_slices": model.n_slices, "queries_per_rank_per_step": n_q,
