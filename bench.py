@@ -518,7 +518,7 @@ def run_ours(a):
             pass
 
     cpu = cpu_oracle_throughput(steps=2, warmup=1) if world == 1 else None  # rank 0 at N = 1 only: two full config-2 iterations
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": n_warm,
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "untimed_iterations_before_each_timed_leg": n_warm,
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
             "data": "synthetic", "config": config_block(world, a.scaling, B if strong else None),
             "workload_detail": {"n_pixels_in_table": int(dataset.xyz.shape[0]), "n_slices": model.n_slices, "queries_per_rank_per_step": n_q,
