@@ -523,7 +523,8 @@ def run_ours(a):
             "data": "synthetic", "config": config_block(world, a.scaling, B if strong else None),
             "workload_detail": {"n_pixels_in_table": int(dataset.xyz.shape[0]), "n_slices": model.n_slices, "queries_per_rank_per_step": n_q,
                                 "global_queries_per_step": n_q * world, "smem_staged_levels": "levels gathered from the TMA-staged shared-memory copy: see DESIGN.md s.4"},
-            "dp": {"mode": trainer.dp_mode, "multimem": bool(getattr(trainer, "dp_multimem_active", False)), "exchange_ms": exchange_ms,
+            "dp": {"mode": trainer.dp_mode, "multimem": bool(getattr(trainer, "dp_multimem_active", False)),
+                   "autotune_ms": getattr(trainer, "dp_autotune_ms", None), "exchange_ms": exchange_ms,
                    "what": "exchange = gradient mean over the ranks + AdamW + fp16 parameter refresh; 'peer' = one fused kernel over NVLink peer memory "
                            "(nsv_adamw_step_dp; multimem: sum and replication inside the NVSwitch through multicast addresses, nsv_adamw_step_dp_mc), "
                            "'allreduce' = NCCL all-reduce + nsv_adamw_step"} if world > 1 else None,

@@ -599,34 +599,23 @@ class FusedTrainer:
             st.grad[: st.n_train].zero_()
             return
         if self.dp_mode == "peer":
-            h = st.peer_handle
             if getattr(self.args, "dp_multimem", None) is None:
                 import os
 
-                # in-switch reduction / replication (NVLS, nsv_adamw_step_dp_mc) is opt-in (NSV_DP_MULTIMEM=1): bit-identical to the
-                # unicast kernel at 2 ranks but slower there (exchange 0.122 vs 0.086 ms on config 2, profiles/r02_dp_multimem_2gpu.json)
-                # -- a reduce-scatter sends (world-1)/world of every rank's gradient whichever side does the adding, so the switch only
-                # relieves the receiving direction, and multimem.ld_reduce has the longer latency
-                self.args.dp_multimem = os.environ.get("NSV_DP_MULTIMEM", "0") == "1"
-            mc = st.mc_ptrs if self.args.dp_multimem else None
-            h.barrier()  # every rank's kernel A has finished: all gradients are complete
-            with torch.cuda.device(st.device):
-                if mc is not None:
-                    rc = _lib.lib().nsv_adamw_step_dp_mc(
-                        _lib.ptr(st.flat), st.peer_grads, _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), st.peer_flat16,
-                        ctypes.c_int(world), ctypes.c_int(rank), ctypes.c_int64(st.n_train), ctypes.c_float(self.lr), ctypes.c_float(0.9),
-                        ctypes.c_float(0.99), ctypes.c_float(1e-15), ctypes.c_float(1e-2), ctypes.c_int(self.iteration),
-                        ctypes.c_float(1.0 / world), ctypes.c_int64(st.tail_lo), st.peer_tail32, ctypes.c_void_p(mc[0]),
-                        ctypes.c_void_p(mc[1]), ctypes.c_void_p(mc[2] or None), _lib.stream(st.device))
+                # unicast peer loads / stores or the NVSwitch-multicast variant (nsv_adamw_step_dp_mc)?  Measured, not guessed:
+                # 2 ranks 0.086 vs 0.122 ms, 4 ranks 0.110 vs 0.111 ms (profiles/r02_dp_multimem_*.json) -- unicast traffic grows with
+                # the number of peers, multicast traffic does not, so the answer depends on the world size and the fabric.
+                # NSV_DP_MULTIMEM=0 / 1 forces one; otherwise a fresh trainer times both on its own box before its first update.
+                env = os.environ.get("NSV_DP_MULTIMEM", "auto")
+                if env in ("0", "1"):
+                    self.args.dp_multimem = env == "1"
+                elif st.mc_ptrs is not None and self.iteration <= 1:
+                    self.args.dp_multimem = self._autotune_multimem(dist, world, rank)
                 else:
-                    rc = _lib.lib().nsv_adamw_step_dp(
-                        _lib.ptr(st.flat), st.peer_grads, _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), st.peer_flat16,
-                        ctypes.c_int(world), ctypes.c_int(rank), ctypes.c_int64(st.n_train), ctypes.c_float(self.lr), ctypes.c_float(0.9),
-                        ctypes.c_float(0.99), ctypes.c_float(1e-15), ctypes.c_float(1e-2), ctypes.c_int(self.iteration),
-                        ctypes.c_float(1.0 / world), ctypes.c_int64(st.tail_lo), st.peer_tail32, _lib.stream(st.device))
-            _lib.check(rc, "nsv_adamw_step_dp_mc" if mc is not None else "nsv_adamw_step_dp")
+                    self.args.dp_multimem = False
+            mc = st.mc_ptrs if self.args.dp_multimem else None
+            self._peer_exchange(world, rank, mc, self.lr, 1.0 / world, self.iteration)
             self.dp_multimem_active = mc is not None
-            h.barrier()  # every owner has read this rank's gradient and written this rank's fp16 parameters
             st.grad[: st.n_train].zero_()
             return
         from .distributed import allreduce_gradient
@@ -638,6 +627,47 @@ class FusedTrainer:
                 ctypes.c_int64(st.n_train), ctypes.c_float(self.lr), ctypes.c_float(0.9), ctypes.c_float(0.99), ctypes.c_float(1e-15),
                 ctypes.c_float(1e-2), ctypes.c_int(self.iteration), ctypes.c_float(unscale), ctypes.c_int(1), _lib.stream(st.device))
         _lib.check(rc, "nsv_adamw_step")
+
+    def _peer_exchange(self, world: int, rank: int, mc, lr: float, unscale: float, step: int) -> None:
+        """barrier | reduce-scatter + AdamW + all-gather in one kernel over peer memory (unicast, or multicast when `mc`) | barrier."""
+        st = self.state
+        h = st.peer_handle
+        h.barrier()  # every rank's kernel A has finished: all gradients are complete
+        common = (_lib.ptr(st.flat), st.peer_grads, _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), st.peer_flat16,
+                  ctypes.c_int(world), ctypes.c_int(rank), ctypes.c_int64(st.n_train), ctypes.c_float(lr), ctypes.c_float(0.9),
+                  ctypes.c_float(0.99), ctypes.c_float(1e-15), ctypes.c_float(1e-2), ctypes.c_int(step),
+                  ctypes.c_float(unscale), ctypes.c_int64(st.tail_lo), st.peer_tail32)
+        with torch.cuda.device(st.device):
+            if mc is not None:
+                rc = _lib.lib().nsv_adamw_step_dp_mc(*common, ctypes.c_void_p(mc[0]), ctypes.c_void_p(mc[1]), ctypes.c_void_p(mc[2] or None),
+                                                     _lib.stream(st.device))
+            else:
+                rc = _lib.lib().nsv_adamw_step_dp(*common, _lib.stream(st.device))
+        _lib.check(rc, "nsv_adamw_step_dp_mc" if mc is not None else "nsv_adamw_step_dp")
+        h.barrier()  # every owner has read this rank's gradient and written this rank's fp16 parameters
+
+    def _autotune_multimem(self, dist, world: int, rank: int) -> bool:
+        """Times the unicast and the multicast exchange on this box (a few launches each, before the first real update) and returns
+        True when multicast is faster on the slowest rank.  The timed launches run with lr = 0 and a zero gradient scale on a trainer
+        whose moments are still zero: parameters, moments and the fp16 / fp32 copies come out bit-identical, the pending gradient is
+        only read."""
+        st = self.state
+        times = []
+        for mc in (None, st.mc_ptrs):
+            for _ in range(2):
+                self._peer_exchange(world, rank, mc, 0.0, 0.0, 1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(8):
+                self._peer_exchange(world, rank, mc, 0.0, 0.0, 1)
+            e1.record()
+            torch.cuda.synchronize(st.device)
+            times.append(e0.elapsed_time(e1) / 8)
+        t = torch.tensor(times, dtype=torch.float32, device=st.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # the same two numbers on every rank: the same choice on every rank
+        uni, mcast = (float(x) for x in t.tolist())
+        self.dp_autotune_ms = {"unicast": uni, "multimem": mcast}
+        return mcast < 0.97 * uni  # ties go to the unicast kernel (bit-identical to all-reduce + AdamW in rank order)
 
     def sync_to_model(self) -> None:
         if self.dp_mode == "peer" and getattr(self.state, "dp_flags", None) is not None and int(self.state.dp_flags[33]) != 0:
