@@ -129,3 +129,27 @@ def test_locality_aware_batch_order_keeps_the_batches():
     ds.count = ds.xyz.shape[0]
     seen = torch.cat([ds.get_batch(256, torch.device("cpu"))["v"] for _ in range(3000 // 256)])
     assert seen.numel() == 2816 and torch.unique(seen).numel() == seen.numel()
+
+
+def test_loss_ring_slots_and_names(native_lib):
+    """FusedState.next_losses: one zeroed 8-float slot per iteration, earlier slots keep their values until the ring wraps, the
+    wrap clears the ring; loss_dict hands out views into the slot under the reference's names (no device work), "MSE+logVar" = word 6
+    (written by the finalize kernel), transReg = word 5."""
+    from nesvor_b200.nesvor import fused as F
+
+    args = make_args()
+    model = build_model(args)
+    st = F.FusedState(model.inr, args, model)
+    assert st.loss_ring.shape == (F.LOSS_RING, 8) and st.losses.data_ptr() == st.loss_ring.data_ptr()
+    a = st.next_losses()
+    a += torch.arange(8.0)
+    names = st.loss_dict(a)
+    assert float(names["MSE"]) == 0.0 and float(names["logVar"]) == 1.0 and float(names["MSE+logVar"]) == 6.0 and float(names["imageReg"]) == 3.0
+    assert all(v.untyped_storage().data_ptr() == st.loss_ring.untyped_storage().data_ptr() for v in names.values())
+    b = st.next_losses()
+    assert b.data_ptr() == a.data_ptr() + 32 and not b.any() and float(a[6]) == 6.0  # a fresh slot; the previous one is intact
+    st.loss_slot = F.LOSS_RING - 1
+    last = st.losses = st.loss_ring[st.loss_slot]
+    last += 1
+    c = st.next_losses()  # wraps
+    assert st.loss_slot == 0 and c.data_ptr() == st.loss_ring.data_ptr() and not st.loss_ring.any()
