@@ -420,15 +420,19 @@ class HostBatchFeeder:
         if nxt is None:
             return
         self.push(nxt)
-        while True:
-            k, batch = self.pop()
-            nxt = next(it, None)
-            if nxt is not None:
-                self.push(nxt)
-            yield batch
-            self.release(k)
-            if nxt is None:
-                return
+        try:
+            while True:
+                k, batch = self.pop()
+                nxt = next(it, None)
+                if nxt is not None:
+                    self.push(nxt)
+                yield batch
+                self.release(k)
+                if nxt is None:
+                    return
+        finally:  # the consumer left the loop early (break / exception): hand the outstanding slots back
+            while self._tail < self._head:
+                self.release(self._tail % self.depth)
 
 
 class FusedTrainer:

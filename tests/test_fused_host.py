@@ -153,3 +153,47 @@ def test_loss_ring_slots_and_names(native_lib):
     last += 1
     c = st.next_losses()  # wraps
     assert st.loss_slot == 0 and c.data_ptr() == st.loss_ring.data_ptr() and not st.loss_ring.any()
+
+
+def test_host_batch_feeder_bookkeeping(monkeypatch):
+    """HostBatchFeeder's slot accounting without a GPU (streams and events stubbed; the overlap itself is a GPU test,
+    tests/test_gpu_e2e.py): batches come out in order, one copy ahead, every slot is handed back -- also when the consumer leaves the
+    loop early --, and `bytes_copied` counts what was copied."""
+    import contextlib
+
+    from nesvor_b200.nesvor import fused as F
+
+    log = []
+
+    class Ev:
+        def record(self, stream=None):
+            log.append("record")
+
+    class Stream:
+        def wait_event(self, ev):
+            log.append("wait")
+
+    monkeypatch.setattr(torch.cuda, "Stream", lambda device=None: Stream())
+    monkeypatch.setattr(torch.cuda, "Event", lambda **kw: Ev())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: Stream())
+    feeder = F.HostBatchFeeder("cpu")
+    host = [{"v": torch.full((4,), float(i)), "slice_idx": torch.full((4,), i, dtype=torch.int64)} for i in range(5)]
+    seen = []
+    for batch in feeder.feed(host):
+        assert feeder._head - feeder._tail in (1, 2)  # this batch + (except at the end) the next one already on its way
+        seen.append((float(batch["v"][0]), int(batch["slice_idx"][0])))
+    assert seen == [(float(i), i) for i in range(5)] and feeder._head == feeder._tail == 5
+    assert feeder.bytes_copied == 5 * (16 + 32)
+    for i, batch in enumerate(feeder.feed(host)):
+        if i == 1:
+            break  # two batches consumed, a third in flight
+    assert feeder._head == feeder._tail  # the generator's clean-up released the outstanding slots
+    assert [float(b["v"][0]) for b in feeder.feed(host[:3])] == [0.0, 1.0, 2.0]
+    assert list(feeder.feed([])) == []
+    with pytest.raises(RuntimeError):
+        feeder.pop()
+    feeder.push(host[0])
+    feeder.push(host[1])
+    with pytest.raises(RuntimeError):
+        feeder.push(host[2])  # depth 2: both slots hold unreleased batches
