@@ -197,3 +197,45 @@ def test_host_batch_feeder_bookkeeping(monkeypatch):
     feeder.push(host[1])
     with pytest.raises(RuntimeError):
         feeder.push(host[2])  # depth 2: both slots hold unreleased batches
+
+
+@pytest.mark.parametrize("t_uni,t_mc,want", [(0.131, 0.105, True), (0.110, 0.111, False), (0.100, 0.098, False)])
+def test_exchange_autotune_decision(native_lib, monkeypatch, t_uni, t_mc, want):
+    """FusedTrainer._autotune_multimem without GPUs: both kernels are launched 2 + 8 times with lr = 0, gradient scale 0, step 1
+    (state-preserving), the timings are max-reduced over the ranks, multicast is taken only when it wins by more than 3 %."""
+    from nesvor_b200.nesvor import fused as F
+
+    args = make_args()
+    tr = F.FusedTrainer(build_model(args), args)
+    tr.state.mc_ptrs = (1 << 40, (1 << 40) + 4096, 0)
+    calls = []
+    monkeypatch.setattr(tr, "_peer_exchange", lambda world, rank, mc, lr, unscale, step: calls.append((mc is not None, lr, unscale, step)))
+    pending = [t_uni * 8, t_mc * 8]
+
+    class Ev:
+        def __init__(self, enable_timing=False):
+            pass
+
+        def record(self, stream=None):
+            pass
+
+        def elapsed_time(self, other):
+            return pending.pop(0)
+
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda device=None: None)
+
+    class Dist:
+        class ReduceOp:
+            MAX = "max"
+
+        reduced = []
+
+        @staticmethod
+        def all_reduce(t, op=None):
+            Dist.reduced.append((t.clone(), op))
+
+    assert tr._autotune_multimem(Dist, 8, 3) is want
+    assert calls == [(False, 0.0, 0.0, 1)] * 10 + [(True, 0.0, 0.0, 1)] * 10
+    assert Dist.reduced[-1][1] == "max" and Dist.reduced[-1][0].numel() == 2
+    assert tr.dp_autotune_ms == pytest.approx({"unicast": t_uni, "multimem": t_mc}, rel=1e-5)
